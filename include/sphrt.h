@@ -1,0 +1,121 @@
+/*
+ * sphrt.h -- C ABI of the B200 line-integration kernels (libsphrt.so).
+ *
+ * Drop-in boundary for the forward / adjoint hot path of Evidlo/sph_raytracer
+ * (sph_raytracer/raytracer.py).  The reference has no native code and no FFI; its
+ * boundary is the Python class `Operator` (raytracer.py:647-755).  Each entry point
+ * below replaces the reference code cited next to it and is what the Python mirror
+ * (sph_raytracer_b200/raytracer.py) binds through ctypes -- see INTEGRATION.md for the
+ * stub a maintainer would add to the reference itself.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - all arrays are dense, C-contiguous; volumes are (n_vol, nr, ne, na), azimuth fastest
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - the library is stateless: it never allocates, frees or synchronises
+ *   - return value: 0 on success, a negative SPHRT_E* code otherwise
+ *     (sphrt_error_string() describes it; CUDA launch errors are SPHRT_ECUDA and the
+ *     cudaError_t is available through sphrt_last_cuda_error())
+ */
+#ifndef SPHRT_H
+#define SPHRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHRT_VERSION 1
+
+enum {
+    SPHRT_OK = 0,
+    SPHRT_EINVAL = -1,     /* null pointer, negative size, unknown dtype ...            */
+    SPHRT_ETOOBIG = -2,    /* a grid axis exceeds SPHRT_MAX_AXIS                        */
+    SPHRT_ESCRATCH = -3,   /* scratch buffer smaller than sphrt_scratch_bytes()         */
+    SPHRT_ECUDA = -4       /* kernel launch failed; see sphrt_last_cuda_error()         */
+};
+
+#define SPHRT_MAX_AXIS 32000   /* voxels per axis (region indices are packed in 16 bits) */
+
+enum { SPHRT_F32 = 0, SPHRT_F64 = 1 };
+
+/* Spherical grid: what Operator reads from SphericalGrid (geometry.py:107-183:
+ * r_b, e_b, a_b, shape) plus trigonometric tables the caller computes ON THE HOST
+ * with the same library the reference uses (torch.cos / torch.sin), so that no libm
+ * difference can move a crossing (raytracer.py:373-375, 452, 505-506). */
+typedef struct sphrt_grid {
+    int32_t nr, ne, na;        /* voxel counts; the boundary vectors hold n+1 values    */
+    int32_t n_c2;              /* entries of c2_sorted                                   */
+    const double *r_b;         /* (nr+1) shell radii, ascending                          */
+    const double *e_b;         /* (ne+1) cone angles from +Z, ascending                  */
+    const double *cos_e;       /* (ne+1) cos(e_b)                                        */
+    const double *a_b;         /* (na+1) half-plane angles from +X, ascending            */
+    const double *cos_a;       /* (na+1) cos(a_b)                                        */
+    const double *sin_a;       /* (na+1) sin(a_b)                                        */
+    const double *c2_sorted;   /* ascending cos(e_b)^2 of the cones with |e-pi/2|>=1e-5  */
+} sphrt_grid;
+
+/* Lines of sight: what Operator reads from ViewGeom (geometry.py:284-288, 389-395,
+ * 494-513): ray i starts at starts[i / rays_per_start] and points along
+ * dirs[i / rays_per_dir] (float64 xyz triples).  rays_per_start == n_rays expresses one
+ * pinhole shared by all pixels, == H*W one pinhole per observation, == 1 explicit
+ * per-ray starts; likewise for directions (parallel beams share one direction).
+ * Directions are used exactly as trace_indices receives them (raytracer.py:48-80). */
+typedef struct sphrt_rays {
+    int64_t n_rays;
+    const double *starts;
+    int64_t rays_per_start;
+    const double *dirs;
+    int64_t rays_per_dir;
+} sphrt_rays;
+
+/* Bytes of scratch the tracing entry points need for this grid (sorted cone-root lists
+ * of rays that run in the equatorial plane or pass close to the origin). */
+int64_t sphrt_scratch_bytes(const sphrt_grid *grid);
+
+/* Operator.__call__ (raytracer.py:692-713) fused with trace_indices (:48-230):
+ *   rays_per_vol == 0 : out[v, i] = sum_seg density[v, vox(seg)] * len(seg)   v < n_vol
+ *                       (static volume, or n_vol channels sharing the geometry)
+ *   rays_per_vol  > 0 : out[i]    = sum_seg density[(i / rays_per_vol) % n_vol, vox] * len
+ *                       (dynamic volume: observation o reads time-slice o, :705-706)
+ * density / out have element type `dtype`; lengths and the accumulation are float64. */
+int sphrt_forward(const sphrt_grid *grid, const sphrt_rays *rays,
+                  const void *density, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                  void *out, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Adjoint: autograd backward of __call__ and Operator.T (raytracer.py:715-748):
+ *   grad[v, vox(seg)] += y[v, i] * len(seg)        (rays_per_vol == 0)
+ *   grad[(i / rays_per_vol) % n_vol, vox] += y[i] * len(seg)   (rays_per_vol > 0)
+ * `grad` is accumulated into (the caller zero-fills it), element type `dtype`. */
+int sphrt_adjoint(const sphrt_grid *grid, const sphrt_rays *rays,
+                  const void *y, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                  void *grad, void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Per-ray number of canonical segments (non-zero length, consecutive identical voxels
+ * merged) = what (Operator.lens > 0) holds after merging; `total` (one uint64, may be
+ * NULL) accumulates their sum.  Used for the ray-segments/s metric. */
+int sphrt_count_segments(const sphrt_grid *grid, const sphrt_rays *rays,
+                         int32_t *count, unsigned long long *total,
+                         void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Debug / parity export of Operator.regs and Operator.lens (raytracer.py:675-679) in
+ * canonical form: vox (n_rays, max_seg, 3) int32 r,e,a; seg_len (n_rays, max_seg) f64;
+ * count (n_rays) true segment count (segments beyond max_seg are dropped). */
+int sphrt_trace_segments(const sphrt_grid *grid, const sphrt_rays *rays, int64_t max_seg,
+                         int32_t *vox, double *seg_len, int32_t *count,
+                         void *scratch, int64_t scratch_bytes, void *stream);
+
+/* find_starts (raytracer.py:605-644): voxel of n points; out is (3, n) int32 with -1
+ * for "outside" exactly like the reference. */
+int sphrt_find_starts(const sphrt_grid *grid, int64_t n, const double *xs, int32_t *out,
+                      void *stream);
+
+int sphrt_version(void);
+const char *sphrt_error_string(int code);
+int sphrt_last_cuda_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHRT_H */

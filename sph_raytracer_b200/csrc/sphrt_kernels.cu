@@ -1,0 +1,457 @@
+// sphrt_kernels.cu -- sm_100a kernels and the C ABI of libsphrt.so (include/sphrt.h).
+//
+// One thread walks one ray with the register-resident crossing merge of
+// sphrt_walker.cuh; nothing per ray-slot is ever materialised (the reference stores
+// 32 B for each of K = 2(Nr+1)+2(Ne+1)+(Na+1)+1 slots per ray, raytracer.py:66-72,230).
+//
+//   forward  : gather-multiply-sum fused with the walk           (Operator.__call__, :692-713)
+//   adjoint  : scatter-add with red.global.add fused with the walk   (Operator.T, :715-748 and
+//              the autograd backward of __call__)
+//   count / trace : parity and metric support (canonical segment lists)
+//
+// Every entry point runs two launches over the same rays:
+//   pass A  one thread per ray, elevation events from the bin tracker; rays that need the
+//           sorted cone-root list (ray_needs_cone_list) are skipped;
+//   pass B  a small persistent grid re-scans the rays and walks only those, each thread
+//           owning a slice of the caller-provided scratch buffer.
+// Boundary tables are staged in shared memory once per block (threads index them
+// divergently, which shared memory serves at full rate and constant memory would not).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo ...
+// (-fmad=false: the walker's arithmetic must not be contracted, see sphrt_walker.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sphrt.h"
+#include "sphrt_walker.cuh"
+
+using namespace sphrt;
+
+namespace {
+
+constexpr int kBlock = 128;            // threads per block, both passes
+constexpr int kListBlocksPerSM = 1;    // pass B: persistent blocks per SM (scratch owners)
+constexpr int kMaxSmemBytes = 160 * 1024;
+
+static int g_last_cuda_error = 0;
+
+struct KRays {
+    int64_t n;
+    const double* starts; int64_t rps;
+    const double* dirs; int64_t rpd;
+};
+
+__host__ __device__ inline int64_t table_doubles(const sphrt_grid& kg)
+{
+    return (int64_t)(kg.nr + 1) + 2 * (int64_t)(kg.ne + 1) + 3 * (int64_t)(kg.na + 1) + kg.n_c2;
+}
+
+// Copy the boundary tables into shared memory (or keep the global pointers when they do not
+// fit) and build the walker's view of the grid.
+__device__ __forceinline__ GridView stage_tables(const sphrt_grid& kg, double* sm, bool use_smem)
+{
+    GridView g;
+    g.nr = kg.nr; g.ne = kg.ne; g.na = kg.na; g.n_c2 = kg.n_c2;
+    if (use_smem) {
+        double* p = sm;
+        const double* src[7] = {kg.r_b, kg.e_b, kg.cos_e, kg.a_b, kg.cos_a, kg.sin_a, kg.c2_sorted};
+        const int cnt[7] = {kg.nr + 1, kg.ne + 1, kg.ne + 1, kg.na + 1, kg.na + 1, kg.na + 1, kg.n_c2};
+        const double* dst[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            dst[k] = p;
+            for (int i = threadIdx.x; i < cnt[k]; i += blockDim.x) p[i] = __ldg(src[k] + i);
+            p += cnt[k];
+        }
+        __syncthreads();
+        g.r_b = dst[0]; g.e_b = dst[1]; g.cos_e = dst[2]; g.a_b = dst[3];
+        g.cos_a = dst[4]; g.sin_a = dst[5]; g.c2_sorted = dst[6];
+    } else {
+        g.r_b = kg.r_b; g.e_b = kg.e_b; g.cos_e = kg.cos_e; g.a_b = kg.a_b;
+        g.cos_a = kg.cos_a; g.sin_a = kg.sin_a; g.c2_sorted = kg.c2_sorted;
+    }
+    // full azimuth range: planes 0 and na are the same half-plane (raytracer.py:528)
+    g.wrap = (-g.a_b[0] == g.a_b[g.na]) && (g.a_b[g.na] == SPHRT_PI);
+    return g;
+}
+
+__device__ __forceinline__ void load_ray(const KRays& kr, int64_t i, double x[3], double d[3])
+{
+    const double* xs = kr.starts + 3 * (i / kr.rps);
+    const double* ds = kr.dirs + 3 * (i / kr.rpd);
+    x[0] = __ldg(xs); x[1] = __ldg(xs + 1); x[2] = __ldg(xs + 2);
+    d[0] = __ldg(ds); d[1] = __ldg(ds + 1); d[2] = __ldg(ds + 2);
+}
+
+// ---- per-ray operations ------------------------------------------------------------------
+
+// volume a ray reads / writes: channel block (static) or time-slice of its observation
+struct VolumeMap {
+    int64_t n_rays, nvox, n_vol, rays_per_vol;
+    int ne, na;
+    __device__ __forceinline__ int64_t offset(int r, int e, int a) const
+    {
+        return ((int64_t)r * ne + e) * na + a;
+    }
+    __device__ __forceinline__ int64_t first_volume(int64_t ray, int ch0) const
+    {
+        return rays_per_vol > 0 ? (ray / rays_per_vol) % n_vol : ch0;
+    }
+};
+
+template <typename T, int NCH>
+struct ForwardOp {
+    const T* density; T* out; VolumeMap m; int ch0;
+    struct Sink {
+        const T* vol; int64_t nvox; int ne, na; int nch;
+        double acc[NCH];
+        __device__ __forceinline__ void segment(int r, int e, int a, double len)
+        {
+            const int64_t idx = ((int64_t)r * ne + e) * na + a;
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                if (c < nch) acc[c] = fma_rn((double)__ldg(vol + c * nvox + idx), len, acc[c]);
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        Sink s;
+        s.vol = density + m.first_volume(ray, ch0) * m.nvox;
+        s.nvox = m.nvox; s.ne = m.ne; s.na = m.na;
+        s.nch = m.rays_per_vol > 0 ? 1 : (int)min((int64_t)NCH, m.n_vol - ch0);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) s.acc[c] = 0.0;
+        return s;
+    }
+    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const
+    {
+        if (m.rays_per_vol > 0) { out[ray] = (T)s.acc[0]; return; }
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
+    }
+    __device__ __forceinline__ void block_end() const {}
+};
+
+template <typename T, int NCH>
+struct AdjointOp {
+    const T* y; T* grad; VolumeMap m; int ch0;
+    struct Sink {
+        T* vol; int64_t nvox; int ne, na; int nch;
+        double w[NCH];
+        __device__ __forceinline__ void segment(int r, int e, int a, double len)
+        {
+            const int64_t idx = ((int64_t)r * ne + e) * na + a;
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                if (c < nch && w[c] != 0.0) atomicAdd(vol + c * nvox + idx, (T)(w[c] * len));
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        Sink s;
+        s.vol = grad + m.first_volume(ray, ch0) * m.nvox;
+        s.nvox = m.nvox; s.ne = m.ne; s.na = m.na;
+        if (m.rays_per_vol > 0) {
+            s.nch = 1;
+            s.w[0] = (double)__ldg(y + ray);
+        } else {
+            s.nch = (int)min((int64_t)NCH, m.n_vol - ch0);
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                s.w[c] = c < s.nch ? (double)__ldg(y + (int64_t)(ch0 + c) * m.n_rays + ray) : 0.0;
+        }
+        return s;
+    }
+    __device__ __forceinline__ void end(int64_t, const Sink&) const {}
+    __device__ __forceinline__ void block_end() const {}
+};
+
+// canonical segment bookkeeping shared by count / trace: consecutive identical voxels merge
+struct CountOp {
+    int32_t* count; unsigned long long* total;
+    struct Sink {
+        int pr, pe, pa; int n;
+        __device__ __forceinline__ void segment(int r, int e, int a, double)
+        {
+            if (n > 0 && r == pr && e == pe && a == pa) return;
+            pr = r; pe = e; pa = a; n++;
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t) const { Sink s; s.pr = s.pe = s.pa = -9; s.n = 0; return s; }
+    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const
+    {
+        count[ray] = s.n;
+        if (total != nullptr && s.n > 0) atomicAdd(total, (unsigned long long)s.n);
+    }
+    __device__ __forceinline__ void block_end() const {}
+};
+
+struct TraceOp {
+    int32_t* vox; double* seg_len; int32_t* count; int64_t max_seg;
+    struct Sink {
+        int32_t* vox; double* len; int64_t max_seg;
+        int pr, pe, pa; int64_t n;
+        __device__ __forceinline__ void segment(int r, int e, int a, double l)
+        {
+            if (n > 0 && r == pr && e == pe && a == pa) {
+                if (n <= max_seg) len[n - 1] += l;
+                return;
+            }
+            if (n < max_seg) { vox[3 * n] = r; vox[3 * n + 1] = e; vox[3 * n + 2] = a; len[n] = l; }
+            pr = r; pe = e; pa = a; n++;
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        Sink s;
+        s.vox = vox + 3 * ray * max_seg; s.len = seg_len + ray * max_seg; s.max_seg = max_seg;
+        s.pr = s.pe = s.pa = -9; s.n = 0;
+        return s;
+    }
+    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const { count[ray] = (int32_t)s.n; }
+    __device__ __forceinline__ void block_end() const {}
+};
+
+// ---- the two passes ------------------------------------------------------------------------
+
+// pass A: one thread per ray, bin-tracker elevation stream
+template <class Op>
+__global__ void __launch_bounds__(kBlock)
+walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kr.n) return;
+    double x[3], d[3];
+    load_ray(kr, i, x, d);
+    RayConsts c;
+    ray_setup(c, x, d);
+    if (ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) return;     // pass B takes it
+    typename Op::Sink sink = op.begin(i);
+    const ConeList none{nullptr, nullptr, 0, 0};
+    walk_ray<false>(g, c, x, none, sink);
+    op.end(i, sink);
+}
+
+// pass B: persistent grid, sorted cone-root list in scratch (slot = global thread id)
+template <class Op>
+__global__ void __launch_bounds__(kBlock)
+walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, double* list_t, int* list_r)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const ConeList list{list_t + tid, list_r + tid, nthreads, 2 * (kg.ne + 1)};
+    for (int64_t i = tid; i < kr.n; i += nthreads) {
+        double x[3], d[3];
+        load_ray(kr, i, x, d);
+        RayConsts c;
+        ray_setup(c, x, d);
+        if (!ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) continue;
+        typename Op::Sink sink = op.begin(i);
+        walk_ray<true>(g, c, x, list, sink);
+        op.end(i, sink);
+    }
+}
+
+__global__ void find_starts_kernel(sphrt_grid kg, int64_t n, const double* xs, int32_t* out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GridView g;
+    g.nr = kg.nr; g.ne = kg.ne; g.na = kg.na; g.wrap = 0;
+    g.r_b = kg.r_b; g.e_b = kg.e_b; g.cos_e = kg.cos_e; g.a_b = kg.a_b;
+    g.cos_a = kg.cos_a; g.sin_a = kg.sin_a; g.c2_sorted = kg.c2_sorted; g.n_c2 = kg.n_c2;
+    const double x[3] = {xs[3 * i], xs[3 * i + 1], xs[3 * i + 2]};
+    int bins[3], st[3];
+    start_voxel(g, x, bins, st);
+    out[i] = st[0]; out[n + i] = st[1]; out[2 * n + i] = st[2];
+}
+
+// ---- host side -------------------------------------------------------------------------------
+
+int num_sms()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        return 148;
+    return sms;
+}
+
+int64_t list_threads() { return (int64_t)num_sms() * kListBlocksPerSM * kBlock; }
+
+int check_grid(const sphrt_grid* g)
+{
+    if (g == nullptr) return SPHRT_EINVAL;
+    if (g->nr < 1 || g->ne < 1 || g->na < 1 || g->n_c2 < 0) return SPHRT_EINVAL;
+    if (g->nr > SPHRT_MAX_AXIS || g->ne > SPHRT_MAX_AXIS || g->na > SPHRT_MAX_AXIS) return SPHRT_ETOOBIG;
+    if (!g->r_b || !g->e_b || !g->cos_e || !g->a_b || !g->cos_a || !g->sin_a) return SPHRT_EINVAL;
+    if (g->n_c2 > 0 && !g->c2_sorted) return SPHRT_EINVAL;
+    return SPHRT_OK;
+}
+
+int check_rays(const sphrt_rays* r)
+{
+    if (r == nullptr || r->n_rays < 0) return SPHRT_EINVAL;
+    if (r->n_rays > 0 && (!r->starts || !r->dirs || r->rays_per_start < 1 || r->rays_per_dir < 1))
+        return SPHRT_EINVAL;
+    return SPHRT_OK;
+}
+
+int cuda_status()
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return SPHRT_ECUDA; }
+    return SPHRT_OK;
+}
+
+template <class Op>
+int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
+                  void* scratch, int64_t scratch_bytes, void* stream)
+{
+    if (rays->n_rays == 0) return SPHRT_OK;
+    if (scratch_bytes < sphrt_scratch_bytes(grid) || scratch == nullptr) return SPHRT_ESCRATCH;
+    cudaStream_t st = (cudaStream_t)stream;
+    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir};
+    const int64_t smem_need = table_doubles(*grid) * (int64_t)sizeof(double);
+    const int use_smem = smem_need <= kMaxSmemBytes;
+    const size_t smem = use_smem ? (size_t)smem_need : 0;
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const int64_t blocks_a = (rays->n_rays + kBlock - 1) / kBlock;
+    if (blocks_a > 0x7fffffffLL) return SPHRT_ETOOBIG;
+    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem, st>>>(*grid, kr, op, use_smem);
+    int rc = cuda_status();
+    if (rc != SPHRT_OK) return rc;
+
+    const int64_t nthreads = list_threads();
+    const int64_t blocks_b = (nthreads / kBlock < blocks_a) ? nthreads / kBlock : blocks_a;
+    double* list_t = (double*)scratch;
+    int* list_r = (int*)(list_t + nthreads * 2 * (int64_t)(grid->ne + 1));
+    walk_listed_kernel<Op><<<(unsigned)blocks_b, kBlock, smem, st>>>(*grid, kr, op, use_smem, list_t, list_r);
+    return cuda_status();
+}
+
+template <template <typename, int> class OpT, typename T>
+int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in, T* out,
+                     int64_t n_vol, int64_t rays_per_vol, bool forward,
+                     void* scratch, int64_t scratch_bytes, void* stream)
+{
+    VolumeMap m;
+    m.n_rays = rays->n_rays; m.nvox = (int64_t)grid->nr * grid->ne * grid->na;
+    m.n_vol = n_vol; m.rays_per_vol = rays_per_vol; m.ne = grid->ne; m.na = grid->na;
+    (void)forward;
+    if (rays_per_vol > 0 || n_vol == 1) {
+        OpT<T, 1> op{in, out, m, 0};
+        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+    }
+    // channels share the geometry: walk once per group of 4 volumes
+    for (int64_t ch0 = 0; ch0 < n_vol; ch0 += 4) {
+        OpT<T, 4> op{in, out, m, (int)ch0};
+        const int rc = launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+        if (rc != SPHRT_OK) return rc;
+    }
+    return SPHRT_OK;
+}
+
+}  // namespace
+
+// ---- C ABI --------------------------------------------------------------------------------------
+
+extern "C" {
+
+int sphrt_version(void) { return SPHRT_VERSION; }
+
+int sphrt_last_cuda_error(void) { return g_last_cuda_error; }
+
+const char* sphrt_error_string(int code)
+{
+    switch (code) {
+    case SPHRT_OK: return "ok";
+    case SPHRT_EINVAL: return "invalid argument";
+    case SPHRT_ETOOBIG: return "grid axis or ray count too large";
+    case SPHRT_ESCRATCH: return "scratch buffer missing or smaller than sphrt_scratch_bytes()";
+    case SPHRT_ECUDA: return "CUDA launch failed";
+    default: return "unknown error";
+    }
+}
+
+int64_t sphrt_scratch_bytes(const sphrt_grid* grid)
+{
+    if (grid == nullptr || grid->ne < 1) return 0;
+    return list_threads() * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
+}
+
+int sphrt_forward(const sphrt_grid* grid, const sphrt_rays* rays, const void* density, int dtype,
+                  int64_t n_vol, int64_t rays_per_vol, void* out, void* scratch,
+                  int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (n_vol < 1 || rays_per_vol < 0) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!density || !out)) return SPHRT_EINVAL;
+    if (dtype == SPHRT_F32)
+        return launch_volume_op<ForwardOp, float>(grid, rays, (const float*)density, (float*)out, n_vol,
+                                                  rays_per_vol, true, scratch, scratch_bytes, stream);
+    if (dtype == SPHRT_F64)
+        return launch_volume_op<ForwardOp, double>(grid, rays, (const double*)density, (double*)out, n_vol,
+                                                   rays_per_vol, true, scratch, scratch_bytes, stream);
+    return SPHRT_EINVAL;
+}
+
+int sphrt_adjoint(const sphrt_grid* grid, const sphrt_rays* rays, const void* y, int dtype,
+                  int64_t n_vol, int64_t rays_per_vol, void* grad, void* scratch,
+                  int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (n_vol < 1 || rays_per_vol < 0) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!y || !grad)) return SPHRT_EINVAL;
+    if (dtype == SPHRT_F32)
+        return launch_volume_op<AdjointOp, float>(grid, rays, (const float*)y, (float*)grad, n_vol,
+                                                  rays_per_vol, false, scratch, scratch_bytes, stream);
+    if (dtype == SPHRT_F64)
+        return launch_volume_op<AdjointOp, double>(grid, rays, (const double*)y, (double*)grad, n_vol,
+                                                   rays_per_vol, false, scratch, scratch_bytes, stream);
+    return SPHRT_EINVAL;
+}
+
+int sphrt_count_segments(const sphrt_grid* grid, const sphrt_rays* rays, int32_t* count,
+                         unsigned long long* total, void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays > 0 && !count) return SPHRT_EINVAL;
+    const CountOp op{count, total};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_trace_segments(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_seg,
+                         int32_t* vox, double* seg_len, int32_t* count, void* scratch,
+                         int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (max_seg < 1) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!vox || !seg_len || !count)) return SPHRT_EINVAL;
+    const TraceOp op{vox, seg_len, count, max_seg};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!xs || !out))) return SPHRT_EINVAL;
+    if (n == 0) return SPHRT_OK;
+    const int64_t blocks = (n + kBlock - 1) / kBlock;
+    find_starts_kernel<<<(unsigned)blocks, kBlock, 0, (cudaStream_t)stream>>>(*grid, n, xs, out);
+    return cuda_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+"""Line-integration operator on a spherical grid -- B200 implementation.
+
+Mirror of the reference's ``sph_raytracer/raytracer.py`` public surface: the class
+``Operator`` (constructor signature, ``__call__``, ``T``, ``grid/geom/device/dynamic``
+attributes, ``repr``; reference ``raytracer.py:647-755``) and ``find_starts``
+(``:605-644``).  Where the reference precomputes and stores, per ray, every candidate
+crossing as ``regs (3,*rays,K) int64`` / ``lens (*rays,K) float64`` (``trace_indices``,
+``:48-230``) and then gathers (``:710-713``), this operator keeps only the rays on the
+GPU and regenerates the crossings inside fused CUDA kernels on every call
+(``csrc/sphrt_kernels.cu`` through the C ABI of ``include/sphrt.h``).
+
+There is no CPU implementation here.  Host tensors are accepted (they are copied to the
+GPU and the result is copied back, so reference-style CPU callers keep working), but
+the arithmetic always runs in the CUDA extension; if it is missing, construction fails.
+"""
+import math
+
+import torch
+
+from . import _cabi
+from .geometry import ViewGeomCollection
+
+__all__ = ["Operator", "find_starts", "DEVICE", "FTYPE", "ITYPE"]
+
+# module defaults, same names as the reference (raytracer.py:12-15)
+DEVICE = "cuda"
+PDEVICE = "cpu"
+FTYPE = torch.float64
+ITYPE = torch.int64
+
+_TAU = float.fromhex("0x1.4f8b588e368f4p-17")      # isclose threshold, raytracer.py:233-246
+_DTYPES = {torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+
+
+def _compute_device(device):
+    """CUDA device that runs the kernels for a user-facing ``device`` argument."""
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        return torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "sph_raytracer_b200 needs a CUDA device: the operator has no CPU implementation")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _GridTables:
+    """Boundary vectors and host-computed trigonometric tables of a SphericalGrid on the GPU.
+
+    cos/sin are evaluated with torch on the host exactly like the reference does
+    (raytracer.py:373-375, 452, 505-506) so that both sides see identical table values.
+    """
+
+    def __init__(self, grid, device):
+        r_b = torch.asarray(grid.r_b, dtype=torch.float64).cpu().reshape(-1)
+        e_b = torch.asarray(grid.e_b, dtype=torch.float64).cpu().reshape(-1)
+        a_b = torch.asarray(grid.a_b, dtype=torch.float64).cpu().reshape(-1)
+        self.nr, self.ne, self.na = len(r_b) - 1, len(e_b) - 1, len(a_b) - 1
+        if min(self.nr, self.ne, self.na) < 1:
+            raise ValueError("grid needs at least one voxel along every axis")
+        cos_e = torch.cos(e_b)
+        c2 = (cos_e * cos_e)[(math.pi / 2 - e_b).abs() >= _TAU]
+        c2_sorted = torch.sort(c2).values
+        parts = [r_b, e_b, cos_e, a_b, torch.cos(a_b), torch.sin(a_b), c2_sorted]
+        self.packed = torch.cat(parts).to(device)
+        base, ptrs = self.packed.data_ptr(), []
+        off = 0
+        for p in parts:
+            ptrs.append(base + 8 * off)
+            off += len(p)
+        self.c = _cabi.Grid(self.nr, self.ne, self.na, len(c2_sorted), *ptrs)
+        self.nvox = self.nr * self.ne * self.na
+
+
+def _compact(t, full_shape):
+    """Represent ``t`` (broadcastable to ``full_shape + (3,)``) as (m, 3) rows plus the number
+    of consecutive rays sharing a row, without materialising the broadcast."""
+    lead = len(full_shape) - (t.dim() - 1)
+    shape = (1,) * lead + tuple(t.shape[:-1])
+    k = len(full_shape)
+    while k > 0 and shape[k - 1] == 1:
+        k -= 1
+    if all(shape[i] == full_shape[i] for i in range(k)):
+        per = math.prod(full_shape[k:])
+        return t.reshape(-1, 3).contiguous(), max(per, 1)
+    return t.broadcast_to(tuple(full_shape) + (3,)).reshape(-1, 3).contiguous(), 1
+
+
+class _Rays:
+    """Ray origins and directions of a view geometry on the GPU (float64)."""
+
+    def __init__(self, geom, device):
+        starts = torch.asarray(geom.ray_starts, dtype=torch.float64)
+        dirs = torch.asarray(geom.rays, dtype=torch.float64)
+        # the reference broadcasts the smaller of the two to the larger (raytracer.py:77-80)
+        full = tuple(starts.shape if starts.numel() > dirs.numel() else dirs.shape)[:-1]
+        if max(starts.dim(), dirs.dim()) - 1 > len(full):
+            raise ValueError(f"ray_starts {tuple(starts.shape)} and rays {tuple(dirs.shape)} "
+                             "cannot be broadcast to a common detector shape")
+        self.shape = tuple(full)
+        self.n = math.prod(self.shape)
+        s, self.rays_per_start = _compact(starts, self.shape)
+        d, self.rays_per_dir = _compact(dirs, self.shape)
+        self.starts, self.dirs = s.to(device), d.to(device)
+        self.c = _cabi.Rays(self.n, self.starts.data_ptr(), self.rays_per_start,
+                            self.dirs.data_ptr(), self.rays_per_dir)
+
+
+class _LineIntegral(torch.autograd.Function):
+    """density -> line integrals; backward is the scatter-add adjoint (the reference gets the
+    same pair implicitly from ATen's index / index_put_)."""
+
+    @staticmethod
+    def forward(ctx, density, op):
+        ctx.op = op
+        ctx.in_shape, ctx.in_device = density.shape, density.device
+        return op._apply_forward(density)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        op = ctx.op
+        grad = op._apply_adjoint(grad_out, ctx.in_shape)
+        return grad.to(ctx.in_device), None
+
+
+class Operator:
+    """Raytracing operator: ``op(density)`` integrates ``density`` along every line of sight.
+
+    Args (same as the reference, raytracer.py:662-665):
+        grid (SphericalGrid): voxel boundaries
+        geom (ViewGeom): lines of sight
+        dynamic (bool): kept for ``repr``; None = True for a ViewGeomCollection
+        ftype: only torch.float64 geometry is implemented (the reference's float32 mode
+            changes which voxels are hit)
+        itype, pdevice: accepted and ignored (nothing is materialised)
+        device: where callers create their tensors.  The kernels always run on a CUDA
+            device (the given one, or the current one if ``device`` is a CPU device)
+        debug, debug_los: print the segment list of one line of sight
+        invalid: not supported (it exposes un-zeroed padding slots that do not exist here)
+        _compute: False skips uploading the geometry
+    """
+
+    def __init__(self, grid, geom, dynamic=False, ftype=FTYPE, itype=ITYPE, device=DEVICE,
+                 pdevice=PDEVICE, debug=False, debug_los=None, invalid=False, _compute=True):
+        self.grid = grid
+        self.geom = geom
+        if dynamic is None:
+            dynamic = isinstance(geom, ViewGeomCollection)
+        self.dynamic = dynamic
+        self.ftype, self.itype, self.device = ftype, itype, device
+        if ftype != torch.float64:
+            raise NotImplementedError("only ftype=torch.float64 geometry is implemented")
+        if invalid:
+            raise NotImplementedError("invalid=True (raw padded slots) has no equivalent here")
+        if not _compute:
+            return
+        self._lib = _cabi.load()
+        self._cdev = _compute_device(device)
+        self._tables = _GridTables(grid, self._cdev)
+        self._rays = _Rays(geom, self._cdev)
+        self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c))
+        if debug:
+            self._print_los(debug_los)
+
+    # ---- launch helpers ---------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self._cdev).cuda_stream
+
+    def _scratch(self):
+        return torch.empty(max(self._scratch_bytes, 8), dtype=torch.uint8, device=self._cdev)
+
+    def _volume_call(self, fn, src, dst, n_vol, rays_per_vol):
+        scratch = self._scratch()
+        with torch.cuda.device(self._cdev):
+            _cabi.check(fn(self._tables.c, self._rays.c, src.data_ptr(), _DTYPES[src.dtype],
+                           n_vol, rays_per_vol, dst.data_ptr(), scratch.data_ptr(),
+                           scratch.numel(), self._stream()))
+
+    # ---- batching rules of Operator.__call__ (raytracer.py:703-713) ---------------------
+    def _plan(self, shape):
+        """(n_vol, rays_per_vol, out_shape, channel_axis) for a density of ``shape``."""
+        t = self._tables
+        G = self._rays.shape
+        if tuple(shape[-3:]) != (t.nr, t.ne, t.na):
+            raise IndexError(f"density shape {tuple(shape)} does not end in the grid shape "
+                             f"{(t.nr, t.ne, t.na)}")
+        if not self.grid.dynamic:
+            batch = tuple(shape[:-3])
+            return math.prod(batch), 0, batch + G, None
+        if len(shape) != 4:
+            raise IndexError("a dynamic grid takes a 4D density (time, r, e, a)")
+        T, g = shape[0], len(G)
+        if g < 3:                                   # every time-slice sees the same rays
+            return T, 0, (T,) + (1,) * (2 - g) + G, None
+        n_obs = G[g - 3]
+        if n_obs == T:                              # observation o reads time-slice o
+            return T, math.prod(G[g - 2:]), G, None
+        if T == 1:
+            return 1, 0, G, None
+        if n_obs == 1:
+            return T, 0, G[:g - 3] + (T,) + G[g - 2:], g - 3
+        raise IndexError(f"shape mismatch: {T} time-slices cannot be broadcast against "
+                         f"{n_obs} observations")
+
+    def _apply_forward(self, density):
+        if density.dtype not in _DTYPES:
+            raise TypeError(f"density dtype {density.dtype} not supported (float32 / float64)")
+        n_vol, rpv, out_shape, ch_axis = self._plan(density.shape)
+        d = density.detach().to(self._cdev).contiguous()
+        n = self._rays.n
+        out = torch.empty((n,) if rpv else (n_vol, n), dtype=d.dtype, device=self._cdev)
+        if n_vol > 0 and n > 0:
+            self._volume_call(self._lib.sphrt_forward, d, out, n_vol, rpv)
+        if ch_axis is not None:
+            G = self._rays.shape
+            out = out.reshape((n_vol,) + G[:ch_axis] + G[ch_axis + 1:]).movedim(0, ch_axis)
+        return out.reshape(out_shape).to(density.device)
+
+    def _apply_adjoint(self, y, density_shape):
+        n_vol, rpv, out_shape, ch_axis = self._plan(density_shape)
+        if y.dtype not in _DTYPES:
+            raise TypeError(f"dtype {y.dtype} not supported (float32 / float64)")
+        yd = y.detach().to(self._cdev).reshape(out_shape)
+        n = self._rays.n
+        if ch_axis is not None:
+            yd = yd.movedim(ch_axis, 0)
+        yd = yd.reshape((n,) if rpv else (n_vol, n)).contiguous()
+        grad = torch.zeros((max(n_vol, 0), self._tables.nr, self._tables.ne, self._tables.na),
+                           dtype=yd.dtype, device=self._cdev)
+        if n_vol > 0 and n > 0:
+            self._volume_call(self._lib.sphrt_adjoint, yd, grad, n_vol, rpv)
+        return grad.reshape(density_shape)
+
+    # ---- public API --------------------------------------------------------------------
+    def __call__(self, density):
+        """Line integrals of ``density``.
+
+        static grid : density ``(*batch, N_r, N_e, N_a)`` -> ``(*batch, *geom.shape)``
+        dynamic grid: density ``(T, N_r, N_e, N_a)``; with a ViewGeomCollection of length T
+                      observation *o* integrates time-slice *o*            -> ``geom.shape``
+        Output dtype and device follow ``density``.  Differentiable w.r.t. ``density``.
+        """
+        return _LineIntegral.apply(density, self)
+
+    def T(self, line_integrations):
+        """Adjoint (back-projection) of the operator for a static grid
+        (reference raytracer.py:715-748)."""
+        if self.grid.dynamic:
+            raise NotImplementedError
+        t = self._tables
+        y = line_integrations
+        if tuple(y.shape) != self._rays.shape:
+            raise IndexError(f"expected line integrals of shape {self._rays.shape}, got {tuple(y.shape)}")
+        return self._apply_adjoint(y, (t.nr, t.ne, t.na)).to(y.device)
+
+    def forward(self, density, out=None):
+        """``op(density)`` without autograd and with an optional preallocated result.
+
+        ``density`` / ``out`` may live on the host; pinned host buffers are copied
+        asynchronously on the current stream and the call returns after the result has
+        landed in ``out`` (this is the end-to-end path timed by bench.py)."""
+        with torch.no_grad():
+            host_in = density.device.type == "cpu"
+            d = density.to(self._cdev, non_blocking=True) if host_in else density
+            y = self._apply_forward(d)
+            if out is None:
+                return y.to(density.device)
+            out.copy_(y.reshape(out.shape), non_blocking=True)
+            if out.device.type == "cpu":
+                torch.cuda.current_stream(self._cdev).synchronize()
+            return out
+
+    def adjoint(self, line_integrations, out=None, density_shape=None):
+        """Back-projection ``A^T y`` without autograd; ``density_shape`` defaults to the
+        grid shape (give ``(C, N_r, N_e, N_a)`` for a multi-channel ``y``)."""
+        with torch.no_grad():
+            t = self._tables
+            shape = tuple(density_shape) if density_shape is not None else tuple(self.grid.shape)
+            y = line_integrations
+            yd = y.to(self._cdev, non_blocking=True) if y.device.type == "cpu" else y
+            g = self._apply_adjoint(yd, shape)
+            if out is None:
+                return g.to(y.device)
+            out.copy_(g.reshape(out.shape), non_blocking=True)
+            if out.device.type == "cpu":
+                torch.cuda.current_stream(self._cdev).synchronize()
+            return out
+
+    def __repr__(self):
+        if self.dynamic:
+            return f"Operator({(self.geom.shape[0], *self.grid.shape)} → {self.geom.shape})"
+        return f"Operator({self.grid.shape} → {self.geom.shape})"
+
+    # ---- parity / metric / debug exports ---------------------------------------------------
+    def segment_counts(self):
+        """Per-ray number of canonical segments (non-zero length, consecutive identical
+        voxels merged) and their total -- the unit of the ray-segments/s metric."""
+        count = torch.empty(self._rays.n, dtype=torch.int32, device=self._cdev)
+        total = torch.zeros(1, dtype=torch.int64, device=self._cdev)
+        scratch = self._scratch()
+        with torch.cuda.device(self._cdev):
+            _cabi.check(self._lib.sphrt_count_segments(
+                self._tables.c, self._rays.c, count.data_ptr(), total.data_ptr(),
+                scratch.data_ptr(), scratch.numel(), self._stream()))
+        return count.reshape(self._rays.shape), int(total.item())
+
+    def segments(self, max_seg=None):
+        """Canonical form of the reference's ``regs`` / ``lens``: ``vox (*rays, max_seg, 3)``
+        int32 (r, e, a), ``lens (*rays, max_seg)`` float64 and ``count (*rays)``."""
+        t = self._tables
+        if max_seg is None:
+            max_seg = 2 * (t.nr + 1) + 2 * (t.ne + 1) + (t.na + 1) + 1
+        n = self._rays.n
+        vox = torch.full((n, max_seg, 3), -9, dtype=torch.int32, device=self._cdev)
+        lens = torch.zeros((n, max_seg), dtype=torch.float64, device=self._cdev)
+        count = torch.zeros(n, dtype=torch.int32, device=self._cdev)
+        scratch = self._scratch()
+        with torch.cuda.device(self._cdev):
+            _cabi.check(self._lib.sphrt_trace_segments(
+                self._tables.c, self._rays.c, max_seg, vox.data_ptr(), lens.data_ptr(),
+                count.data_ptr(), scratch.data_ptr(), scratch.numel(), self._stream()))
+        G = self._rays.shape
+        return vox.reshape(G + (max_seg, 3)), lens.reshape(G + (max_seg,)), count.reshape(G)
+
+    def _print_los(self, los):
+        """debug=True: segment table of one line of sight (reference raytracer.py:175-225)."""
+        vox, lens, count = self.segments()
+        los = tuple(los) if los is not None else (0,) * len(self._rays.shape)
+        k = int(count[los])
+        print("los:", los, "segments:", k)
+        print("  r   e   a        length")
+        for (r, e, a), l in zip(vox[los][:k].tolist(), lens[los][:k].tolist()):
+            print(f"{r:>3} {e:>3} {a:>3}  {l:12.6f}")
+
+    def plot(self, *args, **kwargs):
+        raise NotImplementedError("plotting is outside the scope of the B200 operator")
+
+
+def find_starts(grid, xs, ftype=FTYPE, device=DEVICE):
+    """Voxel index of start points, ``(3, *xs.shape[:-1])`` int64 with -1 = outside
+    (reference raytracer.py:605-644); evaluated by the CUDA extension."""
+    lib = _cabi.load()
+    cdev = _compute_device(device)
+    tables = _GridTables(grid, cdev)
+    pts = torch.asarray(xs, dtype=torch.float64)
+    lead = tuple(pts.shape[:-1])
+    flat = pts.reshape(-1, 3).contiguous().to(cdev)
+    out = torch.empty((3, flat.shape[0]), dtype=torch.int32, device=cdev)
+    with torch.cuda.device(cdev):
+        _cabi.check(lib.sphrt_find_starts(tables.c, flat.shape[0], flat.data_ptr(), out.data_ptr(),
+                                          torch.cuda.current_stream(cdev).cuda_stream))
+    return out.to(torch.int64).reshape((3,) + lead).to(pts.device)

@@ -1,0 +1,50 @@
+// TEST-ONLY host build of the per-ray walker (sph_raytracer_b200/csrc/sphrt_walker.cuh).
+// Lets the crossing-merge algorithm be checked against the oracle and the golden
+// fixtures on a machine without a GPU.  The product never loads this library: the
+// shipped path is the CUDA extension (libsphrt.so) and nothing else.
+//
+// Build (tests/test_walker_host.py does it): g++ -O2 -ffp-contract=off -shared -fPIC
+#include "../sph_raytracer_b200/csrc/sphrt_walker.cuh"
+#include <cstdint>
+#include <vector>
+
+using namespace sphrt;
+
+namespace {
+struct CanonicalSink {
+    int32_t* vox; double* len; int64_t max_seg; int64_t count = 0;
+    int pr = -9, pe = -9, pa = -9;
+    void segment(int r, int e, int a, double l)
+    {
+        if (count > 0 && r == pr && e == pe && a == pa) {
+            if (count <= max_seg) len[count - 1] += l;
+            return;
+        }
+        if (count < max_seg) {
+            vox[3 * count] = r; vox[3 * count + 1] = e; vox[3 * count + 2] = a; len[count] = l;
+        }
+        pr = r; pe = e; pa = a; count++;
+    }
+};
+}  // namespace
+
+extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, const double* e_b,
+                                  const double* cos_e, const double* a_b, const double* cos_a,
+                                  const double* sin_a, const double* c2_sorted, int n_c2,
+                                  int64_t n, const double* xs,
+                                  const double* dirs, int64_t max_seg, int32_t* vox, double* len,
+                                  int32_t* count)
+{
+    GridView g{nr, ne, na, 0, r_b, e_b, cos_e, a_b, cos_a, sin_a, c2_sorted, n_c2};
+    g.wrap = (-a_b[0] == a_b[na]) && (a_b[na] == SPHRT_PI);
+    std::vector<double> lt(2 * (ne + 1)); std::vector<int> lr(2 * (ne + 1));
+    ConeList scratch{lt.data(), lr.data(), 1, 2 * (ne + 1)};
+    for (int64_t i = 0; i < n; i++) {
+        CanonicalSink s{vox + 3 * i * max_seg, len + i * max_seg, max_seg};
+        RayConsts c;
+        ray_setup(c, xs + 3 * i, dirs + 3 * i);
+        if (ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) walk_ray<true>(g, c, xs + 3 * i, scratch, s);
+        else walk_ray<false>(g, c, xs + 3 * i, scratch, s);
+        count[i] = (int32_t)s.count;
+    }
+}
