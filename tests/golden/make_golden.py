@@ -80,7 +80,10 @@ def operator_case(name, grid, starts, rays, density=None, want_grad=False, per_o
         # densities are formulas or seeded (see density_from_seed); not stored
         out["integral"] = y.detach().numpy()
         if want_grad:
-            w = density_from_seed(y.shape, 100 + seed, y.numpy().dtype if False else np.dtype(str(y.dtype).replace("torch.", "")))
+            # adjoint input: seeded weights, zero on the oracle-unstable rays so that the
+            # stored gradient only contains contributions that are graded
+            w = density_from_seed(y.shape, 100 + seed, np.dtype(str(y.dtype).replace("torch.", "")))
+            w = w * torch.from_numpy(stable.reshape(shape)).to(w.dtype)
             (y * w).sum().backward()
             out["grad"] = density.grad.numpy()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)

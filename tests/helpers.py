@@ -57,7 +57,10 @@ def case_density(c):
 
 
 def case_weights(c):
-    return density_from_seed(c.integral.shape, 100, c.integral.dtype)
+    """Adjoint input used by make_golden.py: seeded weights, zero on oracle-unstable rays."""
+    w = density_from_seed(c.integral.shape, 100, c.integral.dtype)
+    shape = tuple(int(v) for v in c.ray_shape)
+    return w * c.stable.reshape(shape).astype(w.dtype)
 
 
 def ragged_equal(c, count, vox, seg_len, mask=None, len_rtol=1e-9, len_atol=1e-12):

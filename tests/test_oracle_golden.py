@@ -91,14 +91,6 @@ def test_oracle_matches_reference_operator(name):
         assert np.allclose(y, 50, atol=1e-2)          # test_raytracer.py:85-116
     if hasattr(c, "grad"):
         w = case_weights(c).reshape(y.shape)
-        w = np.where(st, w, 0).astype(w.dtype)
         g = O.adjoint(og, regs, lens, w, n_vol=dens.reshape(-1, *c.nvox).shape[0], per_ray_vol=prv)
-        if (~c.stable).any():
-            # remove the unstable rays' share from the golden gradient using the oracle itself
-            w_bad = np.where(st, 0, case_weights(c).reshape(y.shape)).astype(w.dtype)
-            g_bad = O.adjoint(og, regs, lens, w_bad, n_vol=g.shape[0], per_ray_vol=prv)
-            want_g = c.grad.reshape(g.shape) - g_bad
-            atol = 1e-3            # unstable rays only approximately removable
-        else:
-            want_g, atol = c.grad.reshape(g.shape), 1e-5 * max(1.0, float(np.abs(c.grad).max()))
-        assert np.allclose(g, want_g, rtol=1e-4, atol=atol), name
+        want_g = c.grad.reshape(g.shape)
+        assert np.allclose(g, want_g, rtol=10 * tol, atol=tol * max(1.0, float(np.abs(want_g).max()))), name
