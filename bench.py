@@ -259,6 +259,9 @@ def run_gpu(args):
     t_fwd = float(np.mean([a.elapsed_time(b) for a, b, c in fwd_ev]))
     t_adj = float(np.mean([b.elapsed_time(c) for a, b, c in fwd_ev]))
     clocks = sampler.summary()
+    if os.environ.get("SPHRT_BENCH_VERBOSE"):
+        print("per-step fwd ms:", [round(a.elapsed_time(b), 3) for a, b, c in fwd_ev],
+              "adj ms:", [round(b.elapsed_time(c), 3) for a, b, c in fwd_ev], file=sys.stderr)
 
     # end-to-end: host buffers in, host buffers out, copies inside the timed region
     step_e2e()

@@ -32,6 +32,8 @@ namespace {
 constexpr int kBlock = 128;            // threads per block, both passes
 constexpr int kListBlocksPerSM = 1;    // pass B: persistent blocks per SM (scratch owners)
 constexpr int kMaxSmemBytes = 160 * 1024;
+constexpr int kQueue = 8;              // pass A: events buffered per stream and thread
+constexpr int kQueueBytes = 3 * kQueue * kBlock * (int)(sizeof(double) + sizeof(int));
 
 static int g_last_cuda_error = 0;
 
@@ -102,29 +104,40 @@ struct VolumeMap {
 template <typename T, int NCH>
 struct ForwardOp {
     const T* density; T* out; VolumeMap m; int ch0;
+    // The gather of segment k is issued when the walker reports it and consumed when it
+    // reports segment k+1, so the L2 latency overlaps one iteration of the event loop.
     struct Sink {
-        const T* vol; int64_t nvox; int ne, na; int nch;
-        double acc[NCH];
+        const T* vol; int nvox; int ne, na; int nch;
+        double acc[NCH], plen;
+        T pval[NCH];
+        __device__ __forceinline__ void flush()
+        {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) acc[c] = fma_rn((double)pval[c], plen, acc[c]);
+        }
         __device__ __forceinline__ void segment(int r, int e, int a, double len)
         {
-            const int64_t idx = ((int64_t)r * ne + e) * na + a;
+            const int idx = (r * ne + e) * na + a;
+            flush();
 #pragma unroll
-            for (int c = 0; c < NCH; c++)
-                if (c < nch) acc[c] = fma_rn((double)__ldg(vol + c * nvox + idx), len, acc[c]);
+            for (int c = 0; c < NCH; c++) pval[c] = c < nch ? __ldg(vol + (size_t)c * nvox + idx) : T(0);
+            plen = len;
         }
     };
     __device__ __forceinline__ Sink begin(int64_t ray) const
     {
         Sink s;
         s.vol = density + m.first_volume(ray, ch0) * m.nvox;
-        s.nvox = m.nvox; s.ne = m.ne; s.na = m.na;
+        s.nvox = (int)m.nvox; s.ne = m.ne; s.na = m.na;
         s.nch = m.rays_per_vol > 0 ? 1 : (int)min((int64_t)NCH, m.n_vol - ch0);
+        s.plen = 0.0;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) s.acc[c] = 0.0;
+        for (int c = 0; c < NCH; c++) { s.acc[c] = 0.0; s.pval[c] = T(0); }
         return s;
     }
-    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const
+    __device__ __forceinline__ void end(int64_t ray, Sink& s) const
     {
+        s.flush();
         if (m.rays_per_vol > 0) { out[ray] = (T)s.acc[0]; return; }
 #pragma unroll
         for (int c = 0; c < NCH; c++)
@@ -137,21 +150,21 @@ template <typename T, int NCH>
 struct AdjointOp {
     const T* y; T* grad; VolumeMap m; int ch0;
     struct Sink {
-        T* vol; int64_t nvox; int ne, na; int nch;
+        T* vol; int nvox; int ne, na; int nch;
         double w[NCH];
         __device__ __forceinline__ void segment(int r, int e, int a, double len)
         {
-            const int64_t idx = ((int64_t)r * ne + e) * na + a;
+            const int idx = (r * ne + e) * na + a;
 #pragma unroll
             for (int c = 0; c < NCH; c++)
-                if (c < nch && w[c] != 0.0) atomicAdd(vol + c * nvox + idx, (T)(w[c] * len));
+                if (c < nch && w[c] != 0.0) atomicAdd(vol + (size_t)c * nvox + idx, (T)(w[c] * len));
         }
     };
     __device__ __forceinline__ Sink begin(int64_t ray) const
     {
         Sink s;
         s.vol = grad + m.first_volume(ray, ch0) * m.nvox;
-        s.nvox = m.nvox; s.ne = m.ne; s.na = m.na;
+        s.nvox = (int)m.nvox; s.ne = m.ne; s.na = m.na;
         if (m.rays_per_vol > 0) {
             s.nch = 1;
             s.w[0] = (double)__ldg(y + ray);
@@ -163,7 +176,7 @@ struct AdjointOp {
         }
         return s;
     }
-    __device__ __forceinline__ void end(int64_t, const Sink&) const {}
+    __device__ __forceinline__ void end(int64_t, Sink&) const {}
     __device__ __forceinline__ void block_end() const {}
 };
 
@@ -179,7 +192,7 @@ struct CountOp {
         }
     };
     __device__ __forceinline__ Sink begin(int64_t) const { Sink s; s.pr = s.pe = s.pa = -9; s.n = 0; return s; }
-    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const
+    __device__ __forceinline__ void end(int64_t ray, Sink& s) const
     {
         count[ray] = s.n;
         if (total != nullptr && s.n > 0) atomicAdd(total, (unsigned long long)s.n);
@@ -209,30 +222,42 @@ struct TraceOp {
         s.pr = s.pe = s.pa = -9; s.n = 0;
         return s;
     }
-    __device__ __forceinline__ void end(int64_t ray, const Sink& s) const { count[ray] = (int32_t)s.n; }
+    __device__ __forceinline__ void end(int64_t ray, Sink& s) const { count[ray] = (int32_t)s.n; }
     __device__ __forceinline__ void block_end() const {}
 };
 
 // ---- the two passes ------------------------------------------------------------------------
 
-// pass A: one thread per ray, bin-tracker elevation stream
+// pass A: one thread per ray, bin-tracker elevation stream, warp-cooperative refills
+struct WarpAny {
+    __device__ __forceinline__ bool operator()(bool p) const { return __any_sync(0xffffffffu, p); }
+};
+
+#ifndef SPHRT_TRACKED_MIN_BLOCKS
+#define SPHRT_TRACKED_MIN_BLOCKS 3
+#endif
 template <class Op>
-__global__ void __launch_bounds__(kBlock)
-walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem)
+__global__ void __launch_bounds__(kBlock, SPHRT_TRACKED_MIN_BLOCKS)
+walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, int table_doubles_smem)
 {
     extern __shared__ double sm_tables[];
     const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
+    // event ring buffers behind the tables: [stream][slot][thread]
+    double* qt = sm_tables + table_doubles_smem + threadIdx.x;
+    int* qr = reinterpret_cast<int*>(sm_tables + table_doubles_smem + 3 * kQueue * kBlock) + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kr.n) return;
-    double x[3], d[3];
-    load_ray(kr, i, x, d);
+    bool active = i < kr.n;
+    double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
     RayConsts c;
-    ray_setup(c, x, d);
-    if (ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) return;     // pass B takes it
-    typename Op::Sink sink = op.begin(i);
-    const ConeList none{nullptr, nullptr, 0, 0};
-    walk_ray<false>(g, c, x, none, sink);
-    op.end(i, sink);
+    if (active) {
+        load_ray(kr, i, x, d);
+        ray_setup(c, x, d);
+        active = !ray_needs_cone_list(c, g.c2_sorted, g.n_c2);     // pass B takes those
+    }
+    const bool mine = active;
+    typename Op::Sink sink = op.begin(mine ? i : 0);
+    walk_ray_queued<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+    if (mine) op.end(i, sink);
 }
 
 // pass B: persistent grid, sorted cone-root list in scratch (slot = global thread id)
@@ -244,7 +269,9 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, double* list_t,
     const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const ConeList list{list_t + tid, list_r + tid, nthreads, 2 * (kg.ne + 1)};
+    // contiguous per-thread lists: the few rays that need them then sort out of L1
+    const int cap = 2 * (kg.ne + 1);
+    const ConeList list{list_t + tid * cap, list_r + tid * cap, 1, cap};
     for (int64_t i = tid; i < kr.n; i += nthreads) {
         double x[3], d[3];
         load_ray(kr, i, x, d);
@@ -289,6 +316,7 @@ int check_grid(const sphrt_grid* g)
     if (g == nullptr) return SPHRT_EINVAL;
     if (g->nr < 1 || g->ne < 1 || g->na < 1 || g->n_c2 < 0) return SPHRT_EINVAL;
     if (g->nr > SPHRT_MAX_AXIS || g->ne > SPHRT_MAX_AXIS || g->na > SPHRT_MAX_AXIS) return SPHRT_ETOOBIG;
+    if ((int64_t)g->nr * g->ne * g->na > 0x7fffffffLL) return SPHRT_ETOOBIG;   // 32-bit voxel offsets
     if (!g->r_b || !g->e_b || !g->cos_e || !g->a_b || !g->cos_a || !g->sin_a) return SPHRT_EINVAL;
     if (g->n_c2 > 0 && !g->c2_sorted) return SPHRT_EINVAL;
     return SPHRT_OK;
@@ -320,13 +348,15 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     const int64_t smem_need = table_doubles(*grid) * (int64_t)sizeof(double);
     const int use_smem = smem_need <= kMaxSmemBytes;
     const size_t smem = use_smem ? (size_t)smem_need : 0;
-    if (smem > 48 * 1024) {
-        cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem_a = smem + kQueueBytes;
+    if (smem_a > 48 * 1024)
+        cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    if (smem > 48 * 1024)
         cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
     const int64_t blocks_a = (rays->n_rays + kBlock - 1) / kBlock;
     if (blocks_a > 0x7fffffffLL) return SPHRT_ETOOBIG;
-    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem, st>>>(*grid, kr, op, use_smem);
+    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem_a, st>>>(*grid, kr, op, use_smem,
+                                                                       (int)(smem / sizeof(double)));
     int rc = cuda_status();
     if (rc != SPHRT_OK) return rc;
 

@@ -333,8 +333,7 @@ SPHRT_HD bool ray_needs_cone_list(const RayConsts& c, const double* c2_sorted, i
     return false;
 }
 
-// Per-thread scratch for the sorted cone-root list; element k of thread slot s lives at
-// index k * stride + s so that a warp touching the same k is coalesced.
+// Per-thread scratch for the sorted cone-root list (element k at [k * stride]).
 struct ConeList {
     double* t; int* r; int64_t stride; int capacity;
     SPHRT_HD double& T(int k) const { return t[(int64_t)k * stride]; }
@@ -600,6 +599,132 @@ SPHRT_HD void walk_ray(const GridView& g, const RayConsts& c, const double x[3],
             as.advance(g, c);
         }
         if (tn > t_prev) t_prev = tn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative variant of walk_ray<false>.
+//
+// In walk_ray every loop iteration consumes one event and immediately regenerates the
+// stream it came from; the 32 rays of a warp sit in different streams at any moment, so
+// the three (expensive, float64) generators execute serially with a third of the lanes
+// each.  Here every stream produces AHEAD into a small per-thread ring buffer, and a
+// buffer is refilled for the whole warp at once when any lane runs dry: the generators
+// run converged, and the consumer loop between refills is a few cheap instructions.
+// The event sequence of each ray -- hence every result -- is identical to walk_ray's.
+//
+// Queue storage is caller-provided: element k of this thread at [k * stride].
+template <int Q, int STRIDE>
+struct EventQueue {
+    double* t; int* r;
+    int head, count, done;          // done: generator exhausted, nothing more will be pushed
+    static constexpr int stride = STRIDE;
+    SPHRT_HD void reset(double* tt, int* rr) { t = tt; r = rr; head = 0; count = 0; done = 0; }
+    SPHRT_HD void push(double tt, int rr)
+    {
+        const int k = (head + count) & (Q - 1);
+        t[k * stride] = tt; r[k * stride] = rr; count++;
+    }
+    SPHRT_HD void pop() { head = (head + 1) & (Q - 1); count--; }
+    SPHRT_HD bool ready() const { return count > 0 || done; }
+    SPHRT_HD double front_t() const { return count > 0 ? t[head * stride] : SPHRT_INF; }
+    SPHRT_HD int front_r() const { return count > 0 ? r[head * stride] : -2; }
+};
+
+// `any(pred)` must be a warp-wide vote in which ALL lanes of the warp take part (lanes
+// without a ray pass active = false); on the host it is the identity.
+template <int Q, int STRIDE, class Sink, class Any>
+SPHRT_HD void walk_ray_queued(const GridView& g, const RayConsts& c, const double x[3], bool active,
+                              double* qt, int* qr, Sink& sink, Any any)
+{
+    constexpr int qstride = STRIDE;
+    int bins[3] = {0, 0, 0}, st[3] = {-1, -1, -1};
+    RadialStream rs; ElevationStream es; AzimuthStream as;
+    EventQueue<Q, STRIDE> qR, qE, qA;
+    qR.reset(qt, qr);
+    qE.reset(qt + Q * qstride, qr + Q * qstride);
+    qA.reset(qt + 2 * Q * qstride, qr + 2 * Q * qstride);
+    const ConeList none{nullptr, nullptr, 0, 0};
+    double t_prev = 0.0;
+
+    if (active) {
+        start_voxel(g, x, bins, st);
+        rs.init(g, c);
+        if (st[0] < 0 && rs.head.t == SPHRT_INF) active = false;      // never enters the grid
+    }
+    if (active) {
+        es.init_tracker(g, c, bins[1]);
+        as.init(g, c, bins[2]);
+        if (st[0] >= 0 && st[1] >= 0 && st[2] >= 0) t_prev = most_negative_candidate(g, c);
+    } else {
+        qR.done = qE.done = qA.done = 1;
+        rs.head.t = es.head.t = as.head.t = SPHRT_INF;
+    }
+    int budget = 4 * (g.nr + g.ne + g.na) + 64;
+
+    while (any(active)) {
+        // ---- refill: whole-warp, one stream at a time ------------------------------------
+        if (any(active && !qR.ready())) {
+            for (int k = 0; k < Q; k++) {
+                const bool need = active && !qR.done && qR.count < Q;
+                if (!any(need)) break;
+                if (need) {
+                    if (rs.head.t == SPHRT_INF) qR.done = 1;
+                    else { qR.push(rs.head.t, rs.head.region); rs.advance(g, c); }
+                }
+            }
+        }
+        if (any(active && !qE.ready())) {
+            for (int k = 0; k < Q; k++) {
+                const bool need = active && !qE.done && qE.count < Q;
+                if (!any(need)) break;
+                if (need) {
+                    if (es.head.t == SPHRT_INF) qE.done = 1;
+                    else { qE.push(es.head.t, es.head.region); es.template advance<false>(g, c, none); }
+                }
+            }
+        }
+        if (any(active && !qA.ready())) {
+            for (int k = 0; k < Q; k++) {
+                const bool need = active && !qA.done && qA.count < Q;
+                if (!any(need)) break;
+                if (need) {
+                    if (as.head.t == SPHRT_INF) qA.done = 1;
+                    else { qA.push(as.head.t, as.head.region); as.advance(g, c); }
+                }
+            }
+        }
+        // ---- consume in lockstep until some lane needs a refill ---------------------------
+        for (;;) {
+            const bool can = active && qR.ready() && qE.ready() && qA.ready();
+            if (any(active && !can)) break;
+            if (!any(active)) break;
+            if (can) {
+                const double tr = qR.front_t(), te = qE.front_t(), ta = qA.front_t();
+                const double tn = fmin(tr, fmin(te, ta));
+                if (st[0] >= 0 && st[1] >= 0 && st[2] >= 0) {
+                    const double len = tn - t_prev;
+                    if (len > 0 && len < SPHRT_INF) sink.segment(st[0], st[1], st[2], len);
+                }
+                if (tn == SPHRT_INF || --budget <= 0) active = false;
+                else if (tr == tn) {
+                    const int reg = qR.front_r();
+                    if (reg != -2) st[0] = reg;
+                    qR.pop();
+                    // left through the outermost shell: nothing further can be valid
+                    if (st[0] < 0 && qR.count == 0 && (qR.done || rs.head.t == SPHRT_INF)) active = false;
+                } else if (te == tn) {
+                    const int reg = qE.front_r();
+                    if (reg != -2) st[1] = reg;
+                    qE.pop();
+                } else {
+                    const int reg = qA.front_r();
+                    if (reg != -2) st[2] = reg;
+                    qA.pop();
+                }
+                if (tn > t_prev) t_prev = tn;
+            }
+        }
     }
 }
 

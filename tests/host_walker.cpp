@@ -28,6 +28,9 @@ struct CanonicalSink {
 };
 }  // namespace
 
+static int g_queued = 0;
+extern "C" void hw_set_queued(int q) { g_queued = q; }
+
 extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, const double* e_b,
                                   const double* cos_e, const double* a_b, const double* cos_a,
                                   const double* sin_a, const double* c2_sorted, int n_c2,
@@ -44,7 +47,11 @@ extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, con
         RayConsts c;
         ray_setup(c, xs + 3 * i, dirs + 3 * i);
         if (ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) walk_ray<true>(g, c, xs + 3 * i, scratch, s);
-        else walk_ray<false>(g, c, xs + 3 * i, scratch, s);
+        else if (!g_queued) walk_ray<false>(g, c, xs + 3 * i, scratch, s);
+        else {
+            double qt[3 * 8]; int qr[3 * 8];
+            walk_ray_queued<8, 1>(g, c, xs + 3 * i, true, qt, qr, s, [](bool p) { return p; });
+        }
         count[i] = (int32_t)s.count;
     }
 }

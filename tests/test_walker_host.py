@@ -50,8 +50,11 @@ def host_trace(hw, og, xs, dirs, max_seg):
     return vox, seg, cnt
 
 
+@pytest.mark.parametrize("queued", [0, 1], ids=["direct", "queued"])
 @pytest.mark.parametrize("name", OPERATOR_CASES)
-def test_walker_matches_golden(hw, name):
+def test_walker_matches_golden(hw, name, queued):
+    """Both walker drivers: the direct merge loop and the warp-cooperative queued one."""
+    hw.hw_set_queued(queued)
     c = load_case(name)
     og = O.OracleGrid(c.grid)
     max_seg = max(int(c.count.max()), 1) + 8
