@@ -1,0 +1,172 @@
+"""CPU tests of the host side: geometry mirror, C-ABI surface, batching plan, sharding.
+No kernel is launched here."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sph_raytracer_b200 as S
+from sph_raytracer_b200 import _cabi, raytracer as R, parallel as P
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libsphrt.so loads and exports exactly the functions include/sphrt.h declares."""
+    from sph_raytracer_b200 import build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "sphrt.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sphrt_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    lib = ctypes.CDLL(build.LIB)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib = _cabi.load()
+    assert lib.sphrt_version() == 1
+    assert lib.sphrt_error_string(-3).decode().startswith("scratch")
+    # argument validation happens before any CUDA call
+    g = _cabi.Grid(0, 1, 1, 0, *([0] * 7))
+    r = _cabi.Rays(0, 0, 1, 0, 1)
+    assert lib.sphrt_forward(g, r, 0, 0, 1, 0, 0, 0, 0, 0) == -1
+    with pytest.raises(_cabi.SphrtError):
+        _cabi.check(-1)
+
+
+def test_operator_requires_cuda_and_rejects_unsupported_modes():
+    grid = S.SphericalGrid((4, 4, 4))
+    geom = S.ViewGeom([-100, 0, 0], [1, 0, 0])
+    with pytest.raises(NotImplementedError):
+        S.Operator(grid, geom, ftype=torch.float32)
+    with pytest.raises(NotImplementedError):
+        S.Operator(grid, geom, invalid=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):          # no CPU fallback
+            S.Operator(grid, geom)
+    op = S.Operator(grid, geom, _compute=False)
+    assert repr(op) == f"Operator({grid.shape} → {geom.shape})"
+    assert op.grid is grid and op.geom is geom and op.dynamic is False
+
+
+def test_compact_ray_layout():
+    """Shared pinholes / directions are stored once per group of rays."""
+    g = S.ConeRectGeom((6, 5), (5, 0, 0))
+    s, per = R._compact(g.ray_starts, (6, 5))
+    assert s.shape == (1, 3) and per == 30
+    coll = sum(S.ConeRectGeom((6, 5), (5 * math.cos(t), 5 * math.sin(t), 1)) for t in (0.1, 0.2, 0.3))
+    s, per = R._compact(coll.ray_starts, (3, 6, 5))
+    assert s.shape == (3, 3) and per == 30
+    d, per = R._compact(coll.rays, (3, 6, 5))
+    assert d.shape == (90, 3) and per == 1
+    pg = S.ParallelGeom((4, 4), (30, 4, 7), size=(2, 2))
+    d, per = R._compact(pg.rays, (4, 4))
+    assert d.shape == (1, 3) and per == 16
+    # a start that varies along a middle axis only cannot be compacted: materialised
+    odd = torch.zeros(1, 6, 1, 3, dtype=torch.float64)
+    s, per = R._compact(odd, (3, 6, 5))
+    assert s.shape == (90, 3) and per == 1
+
+
+class _FakeOp(R.Operator):
+    """Operator with the launch plumbing stubbed out, to exercise the batching plan."""
+
+    def __init__(self, grid, ray_shape):
+        super().__init__(grid, None, _compute=False)
+        self._tables = type("T", (), dict(nr=grid.shape[-3], ne=grid.shape[-2], na=grid.shape[-1]))()
+        self._rays = type("Rr", (), dict(shape=tuple(ray_shape), n=math.prod(ray_shape)))()
+
+
+def test_batching_plan_matches_reference_rules():
+    """Output shapes / time-slice mapping of Operator.__call__ (reference raytracer.py:703-713,
+    SURVEY 3.2)."""
+    st = S.SphericalGrid((2, 3, 4))
+    op = _FakeOp(st, (64, 64))
+    assert op._plan((2, 3, 4)) == (1, 0, (64, 64), None)
+    assert op._plan((10, 2, 3, 4)) == (10, 0, (10, 64, 64), None)
+    assert op._plan((5, 7, 2, 3, 4)) == (35, 0, (5, 7, 64, 64), None)
+    with pytest.raises(IndexError):
+        op._plan((2, 3, 5))
+    dyn = S.SphericalGrid((10, 2, 3, 4))
+    assert _FakeOp(dyn, (64, 64))._plan((10, 2, 3, 4)) == (10, 0, (10, 64, 64), None)
+    assert _FakeOp(dyn, (10, 8, 8))._plan((10, 2, 3, 4)) == (10, 64, (10, 8, 8), None)
+    assert _FakeOp(dyn, (1, 8, 8))._plan((10, 2, 3, 4)) == (10, 0, (10, 8, 8), 0)
+    assert _FakeOp(dyn, (7,))._plan((10, 2, 3, 4)) == (10, 0, (10, 1, 7), None)
+    with pytest.raises(IndexError):
+        _FakeOp(dyn, (9, 8, 8))._plan((10, 2, 3, 4))
+
+
+def test_shard_bounds_cover_everything_once():
+    for n, w in [(1000, 8), (50, 4), (7, 3), (3, 3), (20, 1)]:
+        spans = [P.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        P.shard_bounds(10, 4, 4)
+
+
+# ---- world_size-2 gloo test of the sharded operator (host logic of the multi-GPU path) --------
+class _DenseOp:
+    """CPU stand-in with the Operator interface: y = A x for a fixed random matrix per ray."""
+
+    def __init__(self, grid, geom, **kw):
+        self.grid, self.geom, self.device = grid, geom, "cpu"
+        g = torch.Generator().manual_seed(1234)
+        n_all = 4 * 6                                  # 4 observations of 6 rays in the test
+        A = torch.rand(n_all, math.prod(grid.shape), generator=g, dtype=torch.float64)
+        self.A = torch.cat([A[o.tag * 6:(o.tag + 1) * 6] for o in geom.geoms])
+
+    def __call__(self, density):
+        return (self.A @ density.reshape(-1)).reshape(len(self.geom.geoms), 6)
+
+    def T(self, y):
+        return (self.A.T @ y.reshape(-1)).reshape(tuple(self.grid.shape))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = S.SphericalGrid((2, 3, 4))
+    geoms = []
+    for k in range(4):
+        g = S.ViewGeom(torch.zeros(6, 3), torch.ones(6, 3)); g.tag = k
+        geoms.append(g)
+    coll = S.ViewGeomCollection(*geoms)
+    sop = P.ShardedOperator(grid, coll, _DenseOp)
+    x = torch.arange(24, dtype=torch.float64).reshape(2, 3, 4).requires_grad_(True)
+    y = sop(x)
+    w = torch.ones_like(y) * (rank + 1)
+    (y * w).sum().backward()
+    q.put((rank, sop.lo, sop.hi, y.detach().numpy(), x.grad.numpy(), sop.T(w).numpy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_operator_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(1234)
+    A = torch.rand(24, 24, generator=g, dtype=torch.float64)
+    x = torch.arange(24, dtype=torch.float64)
+    full = (A @ x).reshape(4, 6).numpy()
+    w_full = torch.cat([torch.ones(12) * 1, torch.ones(12) * 2]).double()
+    grad = (A.T @ w_full).reshape(2, 3, 4).numpy()
+    assert [(r[1], r[2]) for r in res] == [(0, 2), (2, 4)]
+    for rank, lo, hi, y, gx, ty in res:
+        assert np.allclose(y, full[lo:hi])
+        assert np.allclose(gx, grad)       # gradient is global (all-reduced) on every rank
+        assert np.allclose(ty, grad)
