@@ -23,7 +23,7 @@
 #include <stdint.h>
 
 #include "../../include/sphrt.h"
-#include "sphrt_walker.cuh"
+#include "sphrt_fast.cuh"
 
 using namespace sphrt;
 
@@ -256,7 +256,7 @@ walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, int table_doub
     }
     const bool mine = active;
     typename Op::Sink sink = op.begin(mine ? i : 0);
-    walk_ray_queued<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+    walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
     if (mine) op.end(i, sink);
 }
 

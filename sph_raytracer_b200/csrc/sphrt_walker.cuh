@@ -534,7 +534,8 @@ SPHRT_HD double most_negative_candidate(const GridView& g, const RayConsts& c)
 
 // start voxel (find_starts + cart2sph, :555-578, 605-644).  bins: geometric bins,
 // state: reference region values.
-SPHRT_HD void start_voxel(const GridView& g, const double x[3], int bins[3], int state[3])
+SPHRT_HD void start_voxel(const GridView& g, const double x[3], int bins[3], int state[3],
+                          double* sph = nullptr)
 {
     const double xy = x[0] * x[0] + x[1] * x[1];
     const double r = sqrt(xy + x[2] * x[2]);
@@ -543,6 +544,15 @@ SPHRT_HD void start_voxel(const GridView& g, const double x[3], int bins[3], int
     bins[0] = locate(g.r_b, g.nr, r, &state[0]);
     bins[1] = locate(g.e_b, g.ne, e, &state[1]);
     bins[2] = locate(g.a_b, g.na, a, &state[2]);
+    if (sph) { sph[0] = r; sph[1] = e; sph[2] = a; }
+}
+
+// true if v lies within `tol` of one of the boundaries of its bin
+SPHRT_HD bool near_boundary(const double* b, int n, int bin, double v, double tol)
+{
+    const int lo = bin < 0 ? 0 : (bin > n ? n : bin);
+    const int hi = bin + 1 > n ? n : (bin + 1 < 0 ? 0 : bin + 1);
+    return fabs(v - b[lo]) < tol || fabs(v - b[hi]) < tol;
 }
 
 // ---------------------------------------------------------------------------------------

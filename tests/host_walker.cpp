@@ -4,7 +4,7 @@
 // shipped path is the CUDA extension (libsphrt.so) and nothing else.
 //
 // Build (tests/test_walker_host.py does it): g++ -O2 -ffp-contract=off -shared -fPIC
-#include "../sph_raytracer_b200/csrc/sphrt_walker.cuh"
+#include "../sph_raytracer_b200/csrc/sphrt_fast.cuh"
 #include <cstdint>
 #include <vector>
 
@@ -50,7 +50,8 @@ extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, con
         else if (!g_queued) walk_ray<false>(g, c, xs + 3 * i, scratch, s);
         else {
             double qt[3 * 8]; int qr[3 * 8];
-            walk_ray_queued<8, 1>(g, c, xs + 3 * i, true, qt, qr, s, [](bool p) { return p; });
+            if (g_queued == 1) walk_ray_queued<8, 1>(g, c, xs + 3 * i, true, qt, qr, s, [](bool p) { return p; });
+            else walk_ray_fast<8, 1>(g, c, xs + 3 * i, true, qt, qr, s, [](bool p) { return p; });
         }
         count[i] = (int32_t)s.count;
     }

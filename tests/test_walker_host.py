@@ -19,12 +19,13 @@ from helpers import OPERATOR_CASES, load_case, ragged_equal
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_walker.cpp")
 HDR = os.path.join(HERE, "..", "sph_raytracer_b200", "csrc", "sphrt_walker.cuh")
+HDR2 = os.path.join(HERE, "..", "sph_raytracer_b200", "csrc", "sphrt_fast.cuh")
 LIB = os.path.join(HERE, "_host_walker.so")
 
 
 @pytest.fixture(scope="session")
 def hw():
-    newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+    newest = max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2))
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared",
                         "-fPIC", "-o", LIB, SRC], check=True)
@@ -50,7 +51,7 @@ def host_trace(hw, og, xs, dirs, max_seg):
     return vox, seg, cnt
 
 
-@pytest.mark.parametrize("queued", [0, 1], ids=["direct", "queued"])
+@pytest.mark.parametrize("queued", [0, 1, 2], ids=["direct", "queued", "fast"])
 @pytest.mark.parametrize("name", OPERATOR_CASES)
 def test_walker_matches_golden(hw, name, queued):
     """Both walker drivers: the direct merge loop and the warp-cooperative queued one."""
