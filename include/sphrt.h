@@ -70,9 +70,11 @@ typedef struct sphrt_rays {
     int64_t rays_per_dir;
 } sphrt_rays;
 
-/* Bytes of scratch the tracing entry points need for this grid (sorted cone-root lists
- * of rays that run in the equatorial plane or pass close to the origin). */
-int64_t sphrt_scratch_bytes(const sphrt_grid *grid);
+/* Bytes of caller-owned scratch the tracing entry points need for this grid and ray count:
+ * one bit per ray (the rays that run in the equatorial plane or pass close to the origin
+ * and are walked from a sorted cone-root list in a second pass) plus, only for grids with
+ * more than ~500 cones, global-memory space for those lists. */
+int64_t sphrt_scratch_bytes(const sphrt_grid *grid, int64_t n_rays);
 
 /* Operator.__call__ (raytracer.py:692-713) fused with trace_indices (:48-230):
  *   rays_per_vol == 0 : out[v, i] = sum_seg density[v, vox(seg)] * len(seg)   v < n_vol

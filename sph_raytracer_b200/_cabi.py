@@ -42,7 +42,8 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB
+    # SPHRT_LIB selects another build of the same extension (kernel tuning experiments)
+    path = path or os.environ.get("SPHRT_LIB") or _build.LIB
     if not os.path.exists(path):
         raise SphrtError(
             f"CUDA extension {path} is missing. Build it with "
@@ -54,7 +55,7 @@ def load(path=None):
     lib.sphrt_error_string.argtypes = [c_int]
     lib.sphrt_last_cuda_error.restype = c_int
     lib.sphrt_scratch_bytes.restype = c_int64
-    lib.sphrt_scratch_bytes.argtypes = [P(Grid)]
+    lib.sphrt_scratch_bytes.argtypes = [P(Grid), c_int64]
     vol_args = [P(Grid), P(Rays), c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
     lib.sphrt_forward.restype = c_int
     lib.sphrt_forward.argtypes = vol_args

@@ -40,7 +40,7 @@ struct FastRadial {
             if (phase == 0 && i < 0) { phase = 1; i = 0; }
             if (phase == 1 && i > g.nr) { phase = 2; return false; }
             const int k = i;
-            const double r = g.r_b[k];
+            const double r = g.r_b()[k];
             const double arg = r * r - c.dperp2;
             if (!(arg >= 0)) {                     // shell not reached (sqrt would be NaN)
                 if (phase == 0) { phase = 1; i = k + 1; } else i = k + 1;
@@ -240,8 +240,8 @@ SPHRT_HD void walk_ray_fast(const GridView& g, const RayConsts& c, const double 
             // A start that sits ON a cone or half-plane makes the reference lose or keep the
             // t ~ 0 crossing by rounding (e.g. single_vantage.py: pos (5,0,0) lies on the
             // equator cone and on the plane a = 0); replay from t = 0 then.
-            const bool on_boundary = near_boundary(g.e_b, g.ne, bins[1], sph[1], 1e-9) ||
-                                     near_boundary(g.a_b, g.na, bins[2], sph[2], 1e-9);
+            const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
+                                     near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
             if (bins[0] == g.nr && has_r && !on_boundary) {
                 // starts outside the outermost shell: jump to the entry point.  Until then
                 // r = -1 and every length is zero; the elevation / azimuth state at entry

@@ -29,10 +29,16 @@ using namespace sphrt;
 
 namespace {
 
-constexpr int kBlock = 128;            // threads per block, both passes
-constexpr int kListBlocksPerSM = 1;    // pass B: persistent blocks per SM (scratch owners)
-constexpr int kMaxSmemBytes = 160 * 1024;
-constexpr int kQueue = 8;              // pass A: events buffered per stream and thread
+#ifndef SPHRT_BLOCK
+#define SPHRT_BLOCK 128
+#endif
+constexpr int kBlock = SPHRT_BLOCK;    // threads per block, both passes
+constexpr int kListBlock = 128;         // pass B: max threads per block
+constexpr int kMaxSmemBytes = 96 * 1024;   // boundary tables must fit in shared memory
+#ifndef SPHRT_QUEUE
+#define SPHRT_QUEUE 8
+#endif
+constexpr int kQueue = SPHRT_QUEUE;    // pass A: events buffered per stream and thread
 constexpr int kQueueBytes = 3 * kQueue * kBlock * (int)(sizeof(double) + sizeof(int));
 
 static int g_last_cuda_error = 0;
@@ -48,32 +54,24 @@ __host__ __device__ inline int64_t table_doubles(const sphrt_grid& kg)
     return (int64_t)(kg.nr + 1) + 2 * (int64_t)(kg.ne + 1) + 3 * (int64_t)(kg.na + 1) + kg.n_c2;
 }
 
-// Copy the boundary tables into shared memory (or keep the global pointers when they do not
-// fit) and build the walker's view of the grid.
-__device__ __forceinline__ GridView stage_tables(const sphrt_grid& kg, double* sm, bool use_smem)
+// Copy the boundary tables into shared memory, packed in GridView order, and build the
+// walker's view of the grid.
+__device__ __forceinline__ GridView stage_tables(const sphrt_grid& kg, double* sm)
 {
     GridView g;
     g.nr = kg.nr; g.ne = kg.ne; g.na = kg.na; g.n_c2 = kg.n_c2;
-    if (use_smem) {
-        double* p = sm;
-        const double* src[7] = {kg.r_b, kg.e_b, kg.cos_e, kg.a_b, kg.cos_a, kg.sin_a, kg.c2_sorted};
-        const int cnt[7] = {kg.nr + 1, kg.ne + 1, kg.ne + 1, kg.na + 1, kg.na + 1, kg.na + 1, kg.n_c2};
-        const double* dst[7];
+    g.tab = sm;
+    const double* src[7] = {kg.r_b, kg.e_b, kg.cos_e, kg.a_b, kg.cos_a, kg.sin_a, kg.c2_sorted};
+    const int cnt[7] = {kg.nr + 1, kg.ne + 1, kg.ne + 1, kg.na + 1, kg.na + 1, kg.na + 1, kg.n_c2};
+    double* p = sm;
 #pragma unroll
-        for (int k = 0; k < 7; k++) {
-            dst[k] = p;
-            for (int i = threadIdx.x; i < cnt[k]; i += blockDim.x) p[i] = __ldg(src[k] + i);
-            p += cnt[k];
-        }
-        __syncthreads();
-        g.r_b = dst[0]; g.e_b = dst[1]; g.cos_e = dst[2]; g.a_b = dst[3];
-        g.cos_a = dst[4]; g.sin_a = dst[5]; g.c2_sorted = dst[6];
-    } else {
-        g.r_b = kg.r_b; g.e_b = kg.e_b; g.cos_e = kg.cos_e; g.a_b = kg.a_b;
-        g.cos_a = kg.cos_a; g.sin_a = kg.sin_a; g.c2_sorted = kg.c2_sorted;
+    for (int k = 0; k < 7; k++) {
+        for (int i = threadIdx.x; i < cnt[k]; i += blockDim.x) p[i] = __ldg(src[k] + i);
+        p += cnt[k];
     }
+    __syncthreads();
     // full azimuth range: planes 0 and na are the same half-plane (raytracer.py:528)
-    g.wrap = (-g.a_b[0] == g.a_b[g.na]) && (g.a_b[g.na] == SPHRT_PI);
+    g.wrap = (-g.a_b()[0] == g.a_b()[g.na]) && (g.a_b()[g.na] == SPHRT_PI);
     return g;
 }
 
@@ -234,14 +232,14 @@ struct WarpAny {
 };
 
 #ifndef SPHRT_TRACKED_MIN_BLOCKS
-#define SPHRT_TRACKED_MIN_BLOCKS 3
+#define SPHRT_TRACKED_MIN_BLOCKS (512 / SPHRT_BLOCK)      /* 16 warps per SM: <= 128 registers */
 #endif
 template <class Op>
 __global__ void __launch_bounds__(kBlock, SPHRT_TRACKED_MIN_BLOCKS)
-walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, int table_doubles_smem)
+walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem, uint32_t* listed_mask)
 {
     extern __shared__ double sm_tables[];
-    const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
+    const GridView g = stage_tables(kg, sm_tables);
     // event ring buffers behind the tables: [stream][slot][thread]
     double* qt = sm_tables + table_doubles_smem + threadIdx.x;
     int* qr = reinterpret_cast<int*>(sm_tables + table_doubles_smem + 3 * kQueue * kBlock) + threadIdx.x;
@@ -252,32 +250,48 @@ walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, int table_doub
     if (active) {
         load_ray(kr, i, x, d);
         ray_setup(c, x, d);
-        active = !ray_needs_cone_list(c, g.c2_sorted, g.n_c2);     // pass B takes those
+        active = !ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);     // pass B takes those
     }
+    // one bit per ray: the rays pass B has to walk (ray index and warp are 32-aligned)
+    const uint32_t listed = __ballot_sync(0xffffffffu, i < kr.n && !active);
+    if ((threadIdx.x & 31) == 0 && i < kr.n) listed_mask[i >> 5] = listed;
     const bool mine = active;
     typename Op::Sink sink = op.begin(mine ? i : 0);
     walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
     if (mine) op.end(i, sink);
 }
 
-// pass B: persistent grid, sorted cone-root list in scratch (slot = global thread id)
+// pass B: persistent warps walk the rays flagged by pass A from a heap-sorted list of all cone
+// roots.  A warp takes one 32-ray mask word at a time (flagged rays come in runs along a
+// detector row, so its lanes fill up); each lane owns a [slot][thread] list column in shared
+// memory, or -- grids with very many cones -- a contiguous slice of global scratch.
 template <class Op>
-__global__ void __launch_bounds__(kBlock)
-walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, double* list_t, int* list_r)
+__global__ void __launch_bounds__(kListBlock)
+walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, int64_t n_words,
+                   int table_doubles_smem, double* glist_t, int* glist_r)
 {
     extern __shared__ double sm_tables[];
-    const GridView g = stage_tables(kg, sm_tables, use_smem != 0);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    // contiguous per-thread lists: the few rays that need them then sort out of L1
+    const GridView g = stage_tables(kg, sm_tables);
     const int cap = 2 * (kg.ne + 1);
-    const ConeList list{list_t + tid * cap, list_r + tid * cap, 1, cap};
-    for (int64_t i = tid; i < kr.n; i += nthreads) {
+    ConeList list;
+    if (glist_t == nullptr) {
+        double* lt = sm_tables + table_doubles_smem;
+        int* lr = reinterpret_cast<int*>(lt + (size_t)cap * blockDim.x);
+        list = ConeList{lt + threadIdx.x, lr + threadIdx.x, (int64_t)blockDim.x, cap};
+    } else {
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        list = ConeList{glist_t + tid * cap, glist_r + tid * cap, 1, cap};
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+        const uint32_t m = __ldg(listed_mask + w);
+        if (!((m >> lane) & 1u)) continue;
+        const int64_t i = (w << 5) + lane;
         double x[3], d[3];
         load_ray(kr, i, x, d);
         RayConsts c;
         ray_setup(c, x, d);
-        if (!ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) continue;
         typename Op::Sink sink = op.begin(i);
         walk_ray<true>(g, c, x, list, sink);
         op.end(i, sink);
@@ -286,12 +300,10 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, int use_smem, double* list_t,
 
 __global__ void find_starts_kernel(sphrt_grid kg, int64_t n, const double* xs, int32_t* out)
 {
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    GridView g;
-    g.nr = kg.nr; g.ne = kg.ne; g.na = kg.na; g.wrap = 0;
-    g.r_b = kg.r_b; g.e_b = kg.e_b; g.cos_e = kg.cos_e; g.a_b = kg.a_b;
-    g.cos_a = kg.cos_a; g.sin_a = kg.sin_a; g.c2_sorted = kg.c2_sorted; g.n_c2 = kg.n_c2;
     const double x[3] = {xs[3 * i], xs[3 * i + 1], xs[3 * i + 2]};
     int bins[3], st[3];
     start_voxel(g, x, bins, st);
@@ -309,7 +321,34 @@ int num_sms()
     return sms;
 }
 
-int64_t list_threads() { return (int64_t)num_sms() * kListBlocksPerSM * kBlock; }
+constexpr int kSmemBudget = 200 * 1024;     // per block, pass B lists + tables
+
+// pass B launch shape: threads per block such that the per-lane cone lists fit in shared
+// memory (0 = they do not: global lists)
+struct ListPlan { int threads; size_t smem; int64_t blocks; bool global_lists; };
+
+ListPlan plan_lists(const sphrt_grid& g, int64_t n_rays)
+{
+    ListPlan p;
+    const size_t tables = (size_t)table_doubles(g) * sizeof(double);
+    const size_t per_thread = (size_t)2 * (g.ne + 1) * (sizeof(double) + sizeof(int));
+    int threads = (int)((kSmemBudget - tables) / per_thread) / 32 * 32;
+    if (threads > kListBlock) threads = kListBlock;
+    p.global_lists = threads < 32;
+    p.threads = p.global_lists ? kListBlock : threads;
+    p.smem = tables + (p.global_lists ? 0 : per_thread * p.threads);
+    int per_sm = (int)((220 * 1024) / (p.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int64_t words = (n_rays + 31) / 32;
+    const int64_t want = (words * 32 + p.threads - 1) / p.threads;
+    p.blocks = (int64_t)num_sms() * per_sm;
+    if (p.blocks > want) p.blocks = want;
+    if (p.blocks < 1) p.blocks = 1;
+    return p;
+}
+
+int64_t mask_bytes(int64_t n_rays) { return ((n_rays + 31) / 32 * 4 + 255) / 256 * 256; }
 
 int check_grid(const sphrt_grid* g)
 {
@@ -317,6 +356,7 @@ int check_grid(const sphrt_grid* g)
     if (g->nr < 1 || g->ne < 1 || g->na < 1 || g->n_c2 < 0) return SPHRT_EINVAL;
     if (g->nr > SPHRT_MAX_AXIS || g->ne > SPHRT_MAX_AXIS || g->na > SPHRT_MAX_AXIS) return SPHRT_ETOOBIG;
     if ((int64_t)g->nr * g->ne * g->na > 0x7fffffffLL) return SPHRT_ETOOBIG;   // 32-bit voxel offsets
+    if (table_doubles(*g) * (int64_t)sizeof(double) > kMaxSmemBytes) return SPHRT_ETOOBIG;   // tables live in smem
     if (!g->r_b || !g->e_b || !g->cos_e || !g->a_b || !g->cos_a || !g->sin_a) return SPHRT_EINVAL;
     if (g->n_c2 > 0 && !g->c2_sorted) return SPHRT_EINVAL;
     return SPHRT_OK;
@@ -342,29 +382,32 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
                   void* scratch, int64_t scratch_bytes, void* stream)
 {
     if (rays->n_rays == 0) return SPHRT_OK;
-    if (scratch_bytes < sphrt_scratch_bytes(grid) || scratch == nullptr) return SPHRT_ESCRATCH;
+    if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
     cudaStream_t st = (cudaStream_t)stream;
     const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir};
-    const int64_t smem_need = table_doubles(*grid) * (int64_t)sizeof(double);
-    const int use_smem = smem_need <= kMaxSmemBytes;
-    const size_t smem = use_smem ? (size_t)smem_need : 0;
+    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
     const size_t smem_a = smem + kQueueBytes;
+    const ListPlan lp = plan_lists(*grid, rays->n_rays);
     if (smem_a > 48 * 1024)
         cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (lp.smem > 48 * 1024)
+        cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
     const int64_t blocks_a = (rays->n_rays + kBlock - 1) / kBlock;
     if (blocks_a > 0x7fffffffLL) return SPHRT_ETOOBIG;
-    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem_a, st>>>(*grid, kr, op, use_smem,
-                                                                       (int)(smem / sizeof(double)));
+    uint32_t* mask = (uint32_t*)scratch;
+    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem_a, st>>>(*grid, kr, op,
+                                                                       (int)(smem / sizeof(double)), mask);
     int rc = cuda_status();
     if (rc != SPHRT_OK) return rc;
 
-    const int64_t nthreads = list_threads();
-    const int64_t blocks_b = (nthreads / kBlock < blocks_a) ? nthreads / kBlock : blocks_a;
-    double* list_t = (double*)scratch;
-    int* list_r = (int*)(list_t + nthreads * 2 * (int64_t)(grid->ne + 1));
-    walk_listed_kernel<Op><<<(unsigned)blocks_b, kBlock, smem, st>>>(*grid, kr, op, use_smem, list_t, list_r);
+    double* glist_t = nullptr;
+    int* glist_r = nullptr;
+    if (lp.global_lists) {
+        glist_t = (double*)((char*)scratch + mask_bytes(rays->n_rays));
+        glist_r = (int*)(glist_t + lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1));
+    }
+    walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
+        *grid, kr, op, mask, (rays->n_rays + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r);
     return cuda_status();
 }
 
@@ -412,10 +455,14 @@ const char* sphrt_error_string(int code)
     }
 }
 
-int64_t sphrt_scratch_bytes(const sphrt_grid* grid)
+int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
 {
-    if (grid == nullptr || grid->ne < 1) return 0;
-    return list_threads() * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
+    if (grid == nullptr || grid->ne < 1 || n_rays < 0) return 0;
+    int64_t bytes = mask_bytes(n_rays);
+    const ListPlan lp = plan_lists(*grid, n_rays);
+    if (lp.global_lists)
+        bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
+    return bytes;
 }
 
 int sphrt_forward(const sphrt_grid* grid, const sphrt_rays* rays, const void* density, int dtype,
@@ -480,7 +527,10 @@ int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32
     if (n < 0 || (n > 0 && (!xs || !out))) return SPHRT_EINVAL;
     if (n == 0) return SPHRT_OK;
     const int64_t blocks = (n + kBlock - 1) / kBlock;
-    find_starts_kernel<<<(unsigned)blocks, kBlock, 0, (cudaStream_t)stream>>>(*grid, n, xs, out);
+    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    find_starts_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(*grid, n, xs, out);
     return cuda_status();
 }
 

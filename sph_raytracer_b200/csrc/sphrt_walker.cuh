@@ -45,17 +45,25 @@ namespace sphrt {
 #define SPHRT_PI 0x1.921fb54442d18p+1
 #define SPHRT_INF (__builtin_huge_val())
 
+// All boundary tables live in ONE packed array (one base register instead of seven):
+//   [ r_b (nr+1) | e_b (ne+1) | cos_e (ne+1) | a_b (na+1) | cos_a (na+1) | sin_a (na+1) | c2_sorted ]
 struct GridView {
     int nr, ne, na;        // voxel counts (boundary tables have n+1 entries)
     int wrap;              // azimuth covers [-pi, pi]: planes 0 and na coincide (:528)
-    const double* r_b;     // shell radii
-    const double* e_b;     // cone angles
-    const double* cos_e;   // cos(e_b), computed by torch on the host
-    const double* a_b;     // half-plane angles
-    const double* cos_a;   // cos(a_b)          "
-    const double* sin_a;   // sin(a_b)          "
-    const double* c2_sorted;   // ascending cos^2(e_b) of the cones with |e - pi/2| >= tau
     int n_c2;
+    const double* tab;
+    SPHRT_HD const double* r_b() const { return tab; }                               // shell radii
+    SPHRT_HD const double* e_b() const { return tab + (nr + 1); }                    // cone angles
+    SPHRT_HD const double* cos_e() const { return tab + (nr + 1) + (ne + 1); }       // torch.cos(e_b)
+    SPHRT_HD const double* a_b() const { return tab + (nr + 1) + 2 * (ne + 1); }     // plane angles
+    SPHRT_HD const double* cos_a() const { return a_b() + (na + 1); }                // torch.cos(a_b)
+    SPHRT_HD const double* sin_a() const { return a_b() + 2 * (na + 1); }            // torch.sin(a_b)
+    // ascending cos^2(e_b) of the cones with |e - pi/2| >= tau
+    SPHRT_HD const double* c2_sorted() const { return a_b() + 3 * (na + 1); }
+    SPHRT_HD static int table_doubles(int nr, int ne, int na, int n_c2)
+    {
+        return (nr + 1) + 2 * (ne + 1) + 3 * (na + 1) + n_c2;
+    }
 };
 
 SPHRT_HD double fma_rn(double a, double b, double c)
@@ -132,7 +140,7 @@ SPHRT_HD void ray_setup(RayConsts& c, const double x[3], const double d_in[3])
 SPHRT_HD Event radial_event(const GridView& g, const RayConsts& c, int i, bool second)
 {
     Event ev;
-    const double r = g.r_b[i];
+    const double r = g.r_b()[i];
     const double t1c = sqrt(r * r - c.dperp2);
     const double t = second ? c.tc + t1c : c.tc - t1c;
     const double p0 = c.r0 * t + c.x0, p1 = c.r1 * t + c.x1, p2 = c.r2 * t + c.x2;
@@ -151,7 +159,7 @@ struct ConeQuad { double aa, bb, cc, delta; };
 SPHRT_HD ConeQuad cone_quadratic(const GridView& g, const RayConsts& c, int i)
 {
     ConeQuad q;
-    const double ce = g.cos_e[i];
+    const double ce = g.cos_e()[i];
     const double c2 = ce * ce;
     q.aa = c.dz2 - c2;
     q.bb = 2 * (c.dzxz - c.dx * c2);
@@ -182,8 +190,8 @@ SPHRT_HD Event cone_event(const GridView& g, const RayConsts& c, int i, double t
     ev.geo = i - neg;
     int region = ev.geo;
     if (fabs(prod) < SPHRT_TAU) region = -2;
-    bool shadow = (p2 >= 0) != (g.cos_e[i] >= 0);
-    if (fabs(SPHRT_HALF_PI - g.e_b[i]) < SPHRT_TAU) shadow = false;
+    bool shadow = (p2 >= 0) != (g.cos_e()[i] >= 0);
+    if (fabs(SPHRT_HALF_PI - g.e_b()[i]) < SPHRT_TAU) shadow = false;
     if (shadow) t = SPHRT_INF;
     if (region == g.ne) region = -1;
     ev.region = region;
@@ -195,7 +203,7 @@ SPHRT_HD Event cone_event(const GridView& g, const RayConsts& c, int i, double t
 SPHRT_HD Event plane_event(const GridView& g, const RayConsts& c, int i)
 {
     Event ev;
-    const double ca = g.cos_a[i], sa = g.sin_a[i];
+    const double ca = g.cos_a()[i], sa = g.sin_a()[i];
     const double num = fma_rn(0.0, c.x2, fma_rn(ca, c.x1, (-sa) * c.x0));
     const double den = fma_rn(0.0, c.d2, fma_rn(ca, c.d1, (-sa) * c.d0));
     double t = -num / den;
@@ -541,9 +549,9 @@ SPHRT_HD void start_voxel(const GridView& g, const double x[3], int bins[3], int
     const double r = sqrt(xy + x[2] * x[2]);
     const double e = atan2(sqrt(xy), x[2]);
     const double a = atan2(x[1], x[0]);
-    bins[0] = locate(g.r_b, g.nr, r, &state[0]);
-    bins[1] = locate(g.e_b, g.ne, e, &state[1]);
-    bins[2] = locate(g.a_b, g.na, a, &state[2]);
+    bins[0] = locate(g.r_b(), g.nr, r, &state[0]);
+    bins[1] = locate(g.e_b(), g.ne, e, &state[1]);
+    bins[2] = locate(g.a_b(), g.na, a, &state[2]);
     if (sph) { sph[0] = r; sph[1] = e; sph[2] = a; }
 }
 
@@ -561,7 +569,7 @@ SPHRT_HD bool near_boundary(const double* b, int n, int bin, double v, double to
 // (trace_indices :150-170), in order of increasing distance.
 //
 // kList selects the elevation event source and must equal
-// ray_needs_cone_list(c, g.c2_sorted, g.n_c2) for the ray; `c` comes from ray_setup().
+// ray_needs_cone_list(c, g.c2_sorted(), g.n_c2) for the ray; `c` comes from ray_setup().
 template <bool kList, class Sink>
 SPHRT_HD void walk_ray(const GridView& g, const RayConsts& c, const double x[3],
                        const ConeList& scratch, Sink& sink)

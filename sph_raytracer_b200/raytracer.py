@@ -157,7 +157,7 @@ class Operator:
         self._cdev = _compute_device(device)
         self._tables = _GridTables(grid, self._cdev)
         self._rays = _Rays(geom, self._cdev)
-        self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c))
+        self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         if debug:
             self._print_los(debug_los)
 

@@ -38,7 +38,11 @@ extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, con
                                   const double* dirs, int64_t max_seg, int32_t* vox, double* len,
                                   int32_t* count)
 {
-    GridView g{nr, ne, na, 0, r_b, e_b, cos_e, a_b, cos_a, sin_a, c2_sorted, n_c2};
+    std::vector<double> tab;
+    auto app = [&](const double* p, int n) { tab.insert(tab.end(), p, p + n); };
+    app(r_b, nr + 1); app(e_b, ne + 1); app(cos_e, ne + 1); app(a_b, na + 1); app(cos_a, na + 1);
+    app(sin_a, na + 1); app(c2_sorted, n_c2);
+    GridView g{nr, ne, na, 0, n_c2, tab.data()};
     g.wrap = (-a_b[0] == a_b[na]) && (a_b[na] == SPHRT_PI);
     std::vector<double> lt(2 * (ne + 1)); std::vector<int> lr(2 * (ne + 1));
     ConeList scratch{lt.data(), lr.data(), 1, 2 * (ne + 1)};
@@ -46,7 +50,7 @@ extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, con
         CanonicalSink s{vox + 3 * i * max_seg, len + i * max_seg, max_seg};
         RayConsts c;
         ray_setup(c, xs + 3 * i, dirs + 3 * i);
-        if (ray_needs_cone_list(c, g.c2_sorted, g.n_c2)) walk_ray<true>(g, c, xs + 3 * i, scratch, s);
+        if (ray_needs_cone_list(c, g.c2_sorted(), g.n_c2)) walk_ray<true>(g, c, xs + 3 * i, scratch, s);
         else if (!g_queued) walk_ray<false>(g, c, xs + 3 * i, scratch, s);
         else {
             double qt[3 * 8]; int qr[3 * 8];
@@ -55,4 +59,19 @@ extern "C" void hw_trace_segments(int nr, int ne, int na, const double* r_b, con
         }
         count[i] = (int32_t)s.count;
     }
+}
+
+// number of rays that take the sorted-cone-list path (pass B) -- diagnostics
+extern "C" int64_t hw_count_listed(int ne, const double* e_b, const double* cos_e,
+                                   const double* c2_sorted, int n_c2, int64_t n, const double* xs,
+                                   const double* dirs)
+{
+    (void)ne; (void)e_b; (void)cos_e;
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; i++) {
+        RayConsts c;
+        ray_setup(c, xs + 3 * i, dirs + 3 * i);
+        k += ray_needs_cone_list(c, c2_sorted, n_c2);
+    }
+    return k;
 }
