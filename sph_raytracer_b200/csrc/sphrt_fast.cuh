@@ -69,6 +69,10 @@ struct FastAzimuth {
     int sector, dir;     // current sector; dir +1 / -1 once known, 0 = exhausted
     double t_next;       // pending event
     int geo_next;
+    // A start that lies exactly ON a half-plane makes BOTH planes of the start sector report a
+    // root ahead (the one at t = 0 does not leave the sector); the later one is parked here.
+    double t_alt;
+    int geo_alt;
 
     SPHRT_HD static int n_sectors(const GridView& g) { return g.wrap ? g.na : g.na + 1; }
     SPHRT_HD static int to_sector(const GridView& g, int geo)
@@ -108,8 +112,8 @@ struct FastAzimuth {
         double ta, tb; int ga, gb;
         eval(g, c, plane_of(g, sector, -1), t_now, false, ta, ga);
         eval(g, c, plane_of(g, sector, +1), t_now, false, tb, gb);
-        if (ta <= tb) { t_next = ta; geo_next = ga; dir = -1; }
-        else          { t_next = tb; geo_next = gb; dir = +1; }
+        if (ta <= tb) { t_next = ta; geo_next = ga; dir = -1; t_alt = tb; geo_alt = gb; }
+        else          { t_next = tb; geo_next = gb; dir = +1; t_alt = ta; geo_alt = ga; }
         if (t_next == SPHRT_INF) dir = 0;
     }
     SPHRT_HD bool next(const GridView& g, const RayConsts& c, double& t, int& region)
@@ -121,7 +125,13 @@ struct FastAzimuth {
         const int expect = dir > 0 ? (sector == nsec - 1 ? 0 : sector + 1)
                                    : (sector == 0 ? nsec - 1 : sector - 1);
         const int ns = to_sector(g, geo_next);
-        if (ns != expect || ns == sector) { dir = 0; return true; }
+        if (ns != expect || ns == sector) {
+            // no move through this plane: continue with the other bounding plane, if any
+            t_next = t_alt; geo_next = geo_alt; t_alt = SPHRT_INF;
+            dir = t_next == SPHRT_INF ? 0 : -dir;
+            return true;
+        }
+        t_alt = SPHRT_INF;
         sector = ns;
         eval(g, c, plane_of(g, sector, dir), t, true, t_next, geo_next);
         if (t_next == SPHRT_INF) dir = 0;

@@ -242,15 +242,19 @@ class Operator:
         return _LineIntegral.apply(density, self)
 
     def T(self, line_integrations):
-        """Adjoint (back-projection) of the operator for a static grid
-        (reference raytracer.py:715-748)."""
-        if self.grid.dynamic:
-            raise NotImplementedError
-        t = self._tables
+        """Adjoint (back-projection) of the operator: ``grid.shape`` volume from line
+        integrals of shape ``geom.shape`` (reference raytracer.py:715-748).
+
+        The reference implements the static case only and raises ``NotImplementedError`` for
+        a dynamic grid; here the dynamic case is the adjoint of the dynamic forward
+        (observation *o* back-projects into time-slice *o*).  Any float32 /
+        float64 input is accepted (the reference needs float64)."""
+        shape = tuple(self.grid.shape)
         y = line_integrations
-        if tuple(y.shape) != self._rays.shape:
-            raise IndexError(f"expected line integrals of shape {self._rays.shape}, got {tuple(y.shape)}")
-        return self._apply_adjoint(y, (t.nr, t.ne, t.na)).to(y.device)
+        want = self._plan(shape)[2]
+        if tuple(y.shape) != tuple(want):
+            raise IndexError(f"expected line integrals of shape {tuple(want)}, got {tuple(y.shape)}")
+        return self._apply_adjoint(y, shape).to(y.device)
 
     def forward(self, density, out=None):
         """``op(density)`` without autograd and with an optional preallocated result.

@@ -190,6 +190,15 @@ def main():
                   density=density_from_seed((3,) + tuple(grid.shape), 3),
                   want_grad=True)
 
+    # --- starts that lie exactly ON a half-plane: pos (5, 0, 1) with an even azimuth count has
+    #     a_b[N/2] == 0.0, so the crossing of that plane ties with the start slot at t = 0 ---
+    g16 = RG.SphericalGrid(shape=(16, 16, 16))
+    geoms16 = [RG.ConeCircGeom((24, 16), (5 * torch.cos(t), 5 * torch.sin(t), 1), fov=(5, 45))
+               for t in torch.linspace(0, 2 * torch.pi, 7)[:6]]
+    operator_case("onplane_16", g16, torch.stack([g.ray_starts.expand(24, 16, 3) for g in geoms16]),
+                  torch.stack([g.rays for g in geoms16]), density=density_from_seed(g16.shape, 9),
+                  want_grad=True)
+
     # --- C4 dynamic_measurements.py: 4 time steps, coarse detector ---
     gdyn = RG.SphericalGrid(shape=(4, 50, 50, 50))
     thetas = torch.linspace(0, 2 * torch.pi, 20)[[0, 5, 11, 17]]
@@ -224,5 +233,62 @@ def main():
                   density=density_from_seed(gh.shape, 8), want_grad=True)
 
 
+
+
+# ---- the retrieval loop that calls forward + adjoint (reference retrieval.gd) ----
+class DenseOp:
+    """Deterministic dense stand-in for an operator (CPU tests of the retrieval loop)."""
+
+    def __init__(self, grid, n_meas=40, seed=11):
+        self.grid, self.device = grid, "cpu"
+        n = int(np.prod(tuple(grid.shape)))
+        self.A = torch.from_numpy(np.random.default_rng(seed).random((n_meas, n)))
+
+    def __call__(self, d):
+        return self.A @ d.reshape(-1).to(self.A.dtype)
+
+
+def retrieval_cases():
+    from sph_raytracer import retrieval as RT, loss as RL, model as RM
+    out = {}
+    # (1) loop logic on a dense operator: loss history must be reproduced exactly on the CPU
+    grid = RG.SphericalGrid(shape=(4, 3, 5))
+    f = DenseOp(grid)
+    truth = density_from_seed(grid.shape, 21, np.float64)
+    y = f(truth)
+    fns = [1 * RL.SquareLoss(), 0.5 * RL.NegRegularizer(), RL.CheaterLoss(truth, use_grad=False)]
+    coeffs, y_fit, losses = RT.gd(f, y, RM.FullyDenseModel(grid), lr=1e-1, loss_fns=fns,
+                                  num_iterations=40, progress_bar=False)
+    out["dense_hist"] = np.array([losses[k] for k in fns])
+    out["dense_coeffs"] = coeffs.detach().numpy()
+    # fixed test volumes of model.py
+    gm = RG.SphericalGrid(shape=(12, 10, 8))
+    out["cubes"] = RM.CubesModel(gm).volume.numpy()
+    out["axes"] = RM.AxisAlignmentModel(gm).volume.numpy()
+
+    # (2) static_retrieval.py scaled down, with the reference operator: 6 observations of a
+    #     (24,16) circular detector, grid 16^3, 30 Adam steps, float64 coefficients
+    grid = RG.SphericalGrid(shape=(16, 16, 16))
+    x = torch.zeros(grid.shape)
+    x[:, 8:, :8] = 1
+    x[:, :8, 8:] = 1
+    geoms = sum(RG.ConeCircGeom((24, 16), (5 * torch.cos(t), 5 * torch.sin(t), 1), fov=(5, 45))
+                for t in torch.linspace(0, 2 * torch.pi, 7)[:6])
+    op = RR.Operator(grid, geoms)
+    meas = op(x)
+    fns = [1 * RL.SquareLoss(), 1 * RL.NegRegularizer()]
+    coeffs, y_fit, losses = RT.gd(op, meas.clone(), RM.FullyDenseModel(grid), lr=1e-1, loss_fns=fns,
+                                  num_iterations=30, progress_bar=False)
+    out["ret_meas"] = meas.detach().numpy()
+    out["ret_hist"] = np.array([losses[k] for k in fns])
+    out["ret_coeffs"] = coeffs.detach().numpy()
+    out["ret_yfit"] = y_fit.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "retrieval.npz"), **out)
+    print("retrieval                dense loss", out["dense_hist"][0][[0, -1]],
+          " operator loss", out["ret_hist"][0][[0, -1]])
+
+
 if __name__ == "__main__":
-    main()
+    if "--retrieval-only" not in sys.argv:
+        main()
+    retrieval_cases()

@@ -10,7 +10,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 OPERATOR_CASES = sorted(
     os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-    if os.path.basename(p) != "known_answers.npz")
+    if os.path.basename(p) not in ("known_answers.npz", "retrieval.npz"))
 
 # seeds / formulas of the volumes used by tests/golden/make_golden.py
 DENSITY = {
@@ -18,6 +18,7 @@ DENSITY = {
     "c2_static_rand_f64": (0, np.float64), "c2_multichannel": (3, np.float32),
     "c4_dynamic": (4, np.float32), "rand_partial": (5, np.float32), "rand_log": (6, np.float32),
     "rand_full_inside": (7, np.float32), "parallel_hollow": (8, np.float32),
+    "onplane_16": (9, np.float32),
 }
 
 

@@ -192,8 +192,12 @@ def test_operator_shapes_and_devices(S):
         assert torch.allclose(yd[o], single, rtol=1e-6, atol=1e-7)
     with pytest.raises(IndexError):
         opd(torch.rand((4, 4, 5, 6)).cuda())
-    with pytest.raises(NotImplementedError):
-        opd.T(yd)
+    # adjoint of the dynamic operator (the reference raises NotImplementedError here)
+    w = torch.rand(3, 8, 8, dtype=torch.float64).cuda()
+    vol64 = vol.double()
+    lhs = (opd(vol64) * w).sum().item()
+    rhs = (vol64 * opd.T(w)).sum().item()
+    assert abs(lhs - rhs) <= 1e-11 * abs(lhs)
 
 
 def test_adjoint_dot_test_and_T(S):
