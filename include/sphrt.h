@@ -71,9 +71,10 @@ typedef struct sphrt_rays {
 } sphrt_rays;
 
 /* Bytes of caller-owned scratch the tracing entry points need for this grid and ray count:
- * one bit per ray (the rays that run in the equatorial plane or pass close to the origin
- * and are walked from a sorted cone-root list in a second pass) plus, only for grids with
- * more than ~500 cones, global-memory space for those lists. */
+ * two bits per ray (the rays that run in the equatorial plane or pass close to the origin
+ * and are walked from a sorted cone-root list in a later pass; the rays the warp-cooperative
+ * walker hands to the per-thread walker) plus, only for grids with more than ~500 cones,
+ * global-memory space for those lists. */
 int64_t sphrt_scratch_bytes(const sphrt_grid *grid, int64_t n_rays);
 
 /* Operator.__call__ (raytracer.py:692-713) fused with trace_indices (:48-230):
@@ -107,6 +108,19 @@ int sphrt_count_segments(const sphrt_grid *grid, const sphrt_rays *rays,
 int sphrt_trace_segments(const sphrt_grid *grid, const sphrt_rays *rays, int64_t max_seg,
                          int32_t *vox, double *seg_len, int32_t *count,
                          void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Parity export of the warp-cooperative walker (the kernel that serves large grids): for
+ * every ray it handles itself, ALL its events in merged order -- the reference's sorted
+ * candidate list (raytracer.py:131-170) restricted to the chord inside the outermost shell:
+ * vox (n_rays, max_ev, 3) int32 voxel after the event, ev_len (n_rays, max_ev) f64 distance
+ * to the next event (0 where the reference zeroes the slot), count (n_rays) number of events.
+ * count[i] is left untouched for rays this walker does not handle (the caller presets -1).
+ * stats (4 x uint64, may be NULL, caller zero-fills): rays walked cooperatively, rays needing
+ * the sorted cone list, rays handed to the per-thread walker, of those: failed verification. */
+int sphrt_trace_events(const sphrt_grid *grid, const sphrt_rays *rays, int64_t max_ev,
+                       int32_t *vox, double *ev_len, int32_t *count,
+                       unsigned long long *stats,
+                       void *scratch, int64_t scratch_bytes, void *stream);
 
 /* find_starts (raytracer.py:605-644): voxel of n points; out is (3, n) int32 with -1
  * for "outside" exactly like the reference. */

@@ -10,6 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = [os.path.join(HERE, "csrc", "sphrt_kernels.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "sphrt_walker.cuh"), os.path.join(HERE, "csrc", "sphrt_fast.cuh"),
+           os.path.join(HERE, "csrc", "sphrt_coop.cuh"),
            os.path.join(HERE, "..", "include", "sphrt.h")]
 LIB = os.path.join(HERE, "libsphrt.so")
 

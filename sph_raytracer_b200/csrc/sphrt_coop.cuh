@@ -1,0 +1,384 @@
+// sphrt_coop.cuh -- warp-cooperative walker: 32 lanes share ONE ray at a time.
+//
+// The per-thread walkers (sphrt_walker.cuh / sphrt_fast.cuh) merge three lazy event streams
+// inside one thread: serial float64 dependency chains, three generators that diverge
+// between the lanes of a warp, and a consumer that spends more instructions on queue
+// bookkeeping than on the segment itself (ncu, profiles/README.md).  For grids with
+// hundreds of crossings per ray the work is turned by 90 degrees here:
+//
+//   phase 0  (one lane per ray, 32 rays per warp)  ray constants, classification, and the
+//            index RANGES of the shells / cones / half-planes the ray can meet between its
+//            entry into and exit from the outermost shell; a 76-byte record per ray in
+//            shared memory.
+//   phase 1  (32 lanes per ray, one ray after the other)
+//            a. every lane evaluates one candidate boundary with the reference's exact
+//               arithmetic (the same radial / cone / plane primitives as the other walkers);
+//               valid roots inside the window are compacted by ballot into three SORTED
+//               per-warp lists in shared memory.  Sorted by construction: shells are met
+//               outermost -> innermost -> outermost, the colatitude along a line is
+//               unimodal (cones are listed from the turning point outwards, first crossings
+//               backwards and second crossings forwards from the middle of the buffer),
+//               the azimuth is monotone;
+//            b. the lists are VERIFIED (ascending t, clean guard candidates at both ends of
+//               every range); a ray that fails any check is handed to the per-thread walker
+//               through a bitmask -- the structural shortcuts are never trusted blindly;
+//            c. the lists are merged with two merge-path passes (elevation + azimuth, then
+//               radial + that): every lane co-ranks the start of its equal share of the
+//               merged sequence and merges it sequentially, carrying the voxel state; every
+//               merged event starts one segment that ends at the next event -- the
+//               reference's sort + forward-fill + diff (raytracer.py:131-151).  Gather /
+//               scatter run lane-parallel, one share of the ray per lane.
+//
+// Equal distances in different families are ordered radial < elevation < azimuth; the
+// reference's order of exact ties is unspecified (unstable sort) and
+// irrelevant for the result (zero-length slots).
+//
+// Device only (warp votes and shuffles).  Handles rays that start outside the outermost
+// shell and not on a cone / half-plane, on grids whose azimuth covers the full circle; every
+// other ray takes the per-thread walker.
+#pragma once
+#include "sphrt_fast.cuh"
+
+namespace sphrt {
+
+#define SPHRT_FULL 0xffffffffu
+
+// Shared-memory layout of one warp (byte offsets from the warp's base), filled in by the host.
+struct CoopPlan {
+    int capR, capE, capA;     // event capacity of the three lists
+    int off_tR, off_tE, off_tA;   // double arrays, capacity + 1 (sentinel)
+    int off_rR, off_rE, off_rA;   // int16 arrays, capacity + 1 (leading slot = state at entry)
+    int capEA, off_tEA, off_sEA;  // merged elevation + azimuth list: t, int32 packed state
+    int off_rec;              // per-ray records: 7 double fields, [field][lane]
+    int warp_bytes;
+    int warps;                // warps per block
+    int table_doubles;
+};
+
+enum { COOP_MISS = 0, COOP_RAY = 1, COOP_LISTED = 2, COOP_TRACKED = 3 };
+
+struct CoopRecord {           // what phase 1 needs to know about a ray (warp-uniform there)
+    double d0, d1, d2, tc, dperp2, nx2, t_turn;
+    int imin;                 // innermost shell reached
+    int e_first, e_count, e_step;     // cone candidates e_first + k * e_step, k < e_count
+    int e_mid;                // slot of the elevation buffer where the two runs meet
+    int a_first, a_count, a_dir;      // plane candidates, in the direction of rotation
+    int se0, sa0;             // elevation / azimuth state at the entry point
+};
+
+__device__ __forceinline__ int coop_bin_e(const GridView& g, const double p[3], double* e_out)
+{
+    const double e = atan2(sqrt(p[0] * p[0] + p[1] * p[1]), p[2]);
+    int st;
+    *e_out = e;
+    return locate(g.e_b(), g.ne, e, &st);
+}
+
+// ---- phase 0: classify one ray and plan its candidate ranges ---------------------------------
+__device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
+                                             const CoopPlan& P, CoopRecord& rec)
+{
+    if (ray_needs_cone_list(c, g.c2_sorted(), g.n_c2)) return COOP_LISTED;
+    if (!g.wrap) return COOP_TRACKED;             // partial azimuth range: gap sector logic
+    int bins[3], st[3];
+    double sph[3];
+    start_voxel(g, x, bins, st, sph);
+    const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
+                             near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+    if (bins[0] != g.nr || on_boundary) return COOP_TRACKED;      // starts inside / on a boundary
+    if (c.dperp2 != c.dperp2) return COOP_MISS;                   // no radial root at all
+    const double rN = g.r_b()[g.nr];
+    const double argN = rN * rN - c.dperp2;
+    if (!(argN >= 0)) return COOP_MISS;                           // passes outside the grid
+    const double sN = sqrt(argN);
+    const double t_in = c.tc - sN, t_out = c.tc + sN;
+    if (t_out < 0) return COOP_MISS;                              // the grid lies behind the start
+    if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return COOP_TRACKED;
+    // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
+    int lo = 0, hi = g.nr;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double r = g.r_b()[mid];
+        if (r * r - c.dperp2 >= 0) hi = mid; else lo = mid + 1;
+    }
+    rec.imin = lo;
+    rec.d0 = c.d0; rec.d1 = c.d1; rec.d2 = c.d2;
+    rec.tc = c.tc; rec.dperp2 = c.dperp2; rec.nx2 = c.nx2;
+
+    // entry / exit points and the voxel state at entry (as walk_ray_fast's fast-forward)
+    const double p[3] = {c.d0 * t_in + c.x0, c.d1 * t_in + c.x1, c.d2 * t_in + c.x2};
+    const double q[3] = {c.d0 * t_out + c.x0, c.d1 * t_out + c.x1, c.d2 * t_out + c.x2};
+    int pb[3], ps[3];
+    double psph[3];
+    start_voxel(g, p, pb, ps, psph);
+    rec.se0 = ps[1]; rec.sa0 = ps[2];
+    double qe;
+    const int qb_e = coop_bin_e(g, q, &qe);
+    const double qa = atan2(q[1], q[0]);
+    int qs_a;
+    const int qb_a = locate(g.a_b(), g.na, qa, &qs_a);
+
+    // ---- elevation: colatitude is unimodal along the chord; turning point at t*
+    const double den = c.d2 * c.dx - c.x2;
+    const double tstar = (c.x2 * c.dx - c.d2 * c.nx2) / den;
+    int first, count, step, mid = 1, up = 0;
+    double t_turn = -SPHRT_INF;
+    if (tstar > t_in && tstar < t_out) {
+        const double m[3] = {c.d0 * tstar + c.x0, c.d1 * tstar + c.x1, c.d2 * tstar + c.x2};
+        double me;
+        const int mb = coop_bin_e(g, m, &me);
+        t_turn = tstar;
+        const int top = pb[1] > qb_e ? pb[1] : qb_e, bot = pb[1] < qb_e ? pb[1] : qb_e;
+        if (me < psph[1]) { step = +1; first = mb; count = top + 2 - mb; }        // dips towards +Z
+        else              { step = -1; first = mb + 1; count = mb + 2 - bot; }    // rises towards -Z
+        // first crossings (entry -> turn) fill the buffer downwards from `mid`, second crossings
+        // (turn -> exit) upwards; a chord's colatitude varies by less than pi in total
+        mid = (pb[1] > mb ? pb[1] - mb : mb - pb[1]) + 2;
+        up = (qb_e > mb ? qb_e - mb : mb - qb_e) + 2;
+    } else if (qe >= psph[1]) { step = +1; first = pb[1]; count = qb_e + 2 - pb[1]; up = count; }
+    else                      { step = -1; first = pb[1] + 1; count = pb[1] + 2 - qb_e; up = count; }
+    if (count < 2 || mid + up + 1 > P.capE) return COOP_TRACKED;
+    rec.e_first = first; rec.e_count = count; rec.e_step = step; rec.t_turn = t_turn; rec.e_mid = mid;
+
+    // ---- azimuth: monotone rotation, direction = sign of (x x d)_z
+    const double cross = c.x0 * c.d1 - c.x1 * c.d0;
+    if (!(fabs(cross) > 1e-9 * sqrt(c.nx2))) return COOP_TRACKED;     // (nearly) through the Z axis
+    const int dir = cross > 0 ? +1 : -1;
+    const int s_in = FastAzimuth::to_sector(g, pb[2]), s_out = FastAzimuth::to_sector(g, qb_a);
+    int sweep = (s_out - s_in) * dir;
+    if (sweep < 0) sweep += g.na;
+    if (sweep > g.na / 2 + 1) sweep = 0;          // rounding put the exit a sector behind the entry
+    rec.a_dir = dir;
+    rec.a_first = dir > 0 ? s_in + 1 : s_in;
+    rec.a_count = sweep + 1;                      // the last candidate is the guard
+    if (rec.a_count > P.capA) return COOP_TRACKED;
+    return COOP_RAY;
+}
+
+// ---- phase 1 ------------------------------------------------------------------------------------
+struct CoopLists {
+    double *tR, *tE, *tA;     // ascending distances; [n] = +inf
+    int16_t *rR, *rE, *rA;    // region after the event; [-1] = state at entry
+    int nR, nE, nA;
+};
+
+// Build the three sorted lists of ray `rec`.  Returns false if a structural assumption did not
+// hold (the ray then goes to the per-thread walker).  All lanes of the warp call this.
+__device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P, char* wbase,
+                                           const CoopRecord& rec, const double x[3], int lane,
+                                           CoopLists& L)
+{
+    RayConsts c;
+    c.x0 = x[0]; c.x1 = x[1]; c.x2 = x[2];
+    c.d0 = rec.d0; c.d1 = rec.d1; c.d2 = rec.d2;
+    c.tc = rec.tc; c.dperp2 = rec.dperp2; c.nx2 = rec.nx2;
+    c.dz2 = c.d2 * c.d2;
+    c.dzxz = c.d2 * c.x2;
+    c.dx = dot3(c.d0, c.d1, c.d2, c.x0, c.x1, c.x2);
+    c.xz2 = c.x2 * c.x2;
+    c.r0 = c.r1 = c.r2 = 0.0;                      // only needed by the tangent test (bails out)
+    bool bad = false;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // ---- radial: first roots of shells nr .. imin, then second roots of imin .. nr
+    double* tR = reinterpret_cast<double*>(wbase + P.off_tR);
+    int16_t* rR = reinterpret_cast<int16_t*>(wbase + P.off_rR) + 1;
+    const int m = g.nr - rec.imin + 1;
+    const int nR = 2 * m;
+    const double tang = 1e-17 * (1.0 + c.nx2);
+    for (int k = lane; k < nR; k += 32) {
+        const bool out = k >= m;
+        const int i = out ? rec.imin + (k - m) : g.nr - k;
+        const double r = g.r_b()[i];
+        const double r2 = r * r;
+        const double arg = r2 - c.dperp2;
+        const double t1c = sqrt(arg);
+        const double tt = out ? c.tc + t1c : c.tc - t1c;
+        const int reg = out ? i : i - 1;
+        // tangent within rounding: the reference decides the region from the sign of d.p
+        if (!(arg >= tang + 1e-17 * r2)) bad = true;
+        tR[k] = tt;
+        rR[k] = (int16_t)(reg == g.nr ? -1 : reg);
+    }
+    if (lane == 0) { tR[nR] = SPHRT_INF; rR[-1] = -1; }
+    __syncwarp();
+    const double t_in = tR[0], t_out = tR[nR - 1];
+
+    // ---- elevation: candidates from the turning point outwards
+    double* tEbuf = reinterpret_cast<double*>(wbase + P.off_tE);
+    int16_t* rEbuf = reinterpret_cast<int16_t*>(wbase + P.off_rE) + 1;
+    int nDown = 0, nUp = 0;
+    bool unchanged = false;
+    for (int k0 = 0; k0 < rec.e_count; k0 += 32) {
+        const int k = k0 + lane;
+        const int i = rec.e_first + k * rec.e_step;
+        double ta = SPHRT_INF, tb = SPHRT_INF;
+        int ra = 0, rb = 0;
+        if (k < rec.e_count && i >= 0 && i <= g.ne) {
+            const ConeQuad q = cone_quadratic(g, c, i);
+            double t1, t2;
+            cone_roots(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
+            if (t1 >= t_in && t1 <= t_out) { const Event e = cone_event(g, c, i, t1); ta = e.t; ra = e.region; }
+            if (t2 >= t_in && t2 <= t_out) { const Event e = cone_event(g, c, i, t2); tb = e.t; rb = e.region; }
+            if (tb < ta) { const double tt = ta; ta = tb; tb = tt; const int rr = ra; ra = rb; rb = rr; }
+            if (tb == ta) tb = SPHRT_INF;                      // merged double root: one event
+            // the candidates at both ends of the range are guards: they must stay silent
+            if ((k == 0 || k == rec.e_count - 1) && ta < SPHRT_INF) bad = true;
+        }
+        const bool a_down = ta < rec.t_turn;                    // first crossing (towards the turn)
+        const bool a_up = ta < SPHRT_INF && !a_down;
+        const bool b_up = tb < SPHRT_INF;
+        if (a_up && b_up) bad = true;                           // two crossings after the turn
+        const uint32_t md = __ballot_sync(SPHRT_FULL, a_down);
+        const uint32_t mu = __ballot_sync(SPHRT_FULL, a_up || b_up);
+        if (a_down) {
+            const int slot = rec.e_mid - 1 - (nDown + __popc(md & lt_mask));
+            if (slot >= 0) { tEbuf[slot] = ta; rEbuf[slot] = (int16_t)ra; } else bad = true;
+            unchanged |= ra == -2;
+        }
+        if (a_up || b_up) {
+            const int slot = rec.e_mid + nUp + __popc(mu & lt_mask);
+            if (slot < P.capE) { tEbuf[slot] = a_up ? ta : tb; rEbuf[slot] = (int16_t)(a_up ? ra : rb); }
+            else bad = true;
+            unchanged |= (a_up ? ra : rb) == -2;
+        }
+        nDown += __popc(md); nUp += __popc(mu);
+    }
+    if (__any_sync(SPHRT_FULL, bad)) return false;        // (also keeps the offsets below in range)
+    double* tE = tEbuf + (rec.e_mid - nDown);
+    int16_t* rE = rEbuf + (rec.e_mid - nDown);
+    const int nE = nDown + nUp;
+    if (lane == 0) { tE[nE] = SPHRT_INF; rE[-1] = (int16_t)rec.se0; }
+
+    // ---- azimuth: planes in the direction of rotation
+    double* tA = reinterpret_cast<double*>(wbase + P.off_tA);
+    int16_t* rA = reinterpret_cast<int16_t*>(wbase + P.off_rA) + 1;
+    int nA = 0;
+    for (int k0 = 0; k0 < rec.a_count; k0 += 32) {
+        const int k = k0 + lane;
+        double t = SPHRT_INF;
+        int geo = 0;
+        if (k < rec.a_count) {
+            int pl = rec.a_first + k * rec.a_dir;              // seam: plane na going up, 0 going down
+            if (pl > g.na) pl -= g.na;
+            if (pl < 0) pl += g.na;
+            FastAzimuth::eval(g, c, pl, t_in, false, t, geo);
+            if (!(t <= t_out)) t = SPHRT_INF;
+            if (k == rec.a_count - 1 && t < SPHRT_INF) bad = true;     // guard
+        }
+        const uint32_t mv = __ballot_sync(SPHRT_FULL, t < SPHRT_INF);
+        if (t < SPHRT_INF) {
+            const int slot = nA + __popc(mv & lt_mask);
+            tA[slot] = t; rA[slot] = (int16_t)FastAzimuth::to_region(g, geo);
+        }
+        nA += __popc(mv);
+    }
+    if (lane == 0) { tA[nA] = SPHRT_INF; rA[-1] = (int16_t)rec.sa0; }
+    __syncwarp();
+
+    // ---- verify: ascending lists
+    for (int k = lane; k < nE - 1; k += 32) bad |= !(tE[k] <= tE[k + 1]);
+    for (int k = lane; k < nA - 1; k += 32) bad |= !(tA[k] <= tA[k + 1]);
+    if (nE + nA > P.capEA) bad = true;
+    if (__any_sync(SPHRT_FULL, bad)) return false;
+    // glancing crossings leave the elevation index unchanged (region -2): forward-fill
+    if (__any_sync(SPHRT_FULL, unchanged)) {
+        if (lane == 0)
+            for (int k = 0; k < nE; k++) if (rE[k] == -2) rE[k] = rE[k - 1];
+        __syncwarp();
+    }
+    L.tR = tR; L.tE = tE; L.tA = tA; L.rR = rR; L.rE = rE; L.rA = rA;
+    L.nR = nR; L.nE = nE; L.nA = nA;
+    return true;
+}
+
+// ---- merging -----------------------------------------------------------------------------------
+// Merge path: lane L owns the merged ranks [L*c, (L+1)*c) of two ascending lists and finds where
+// that range starts in each list with one co-rank search; the c-step sequential merge that
+// follows has the same trip count in every lane.  X wins ties (radial < elevation < azimuth).
+
+// number of X entries among the first g entries of merge(X, Y); `steps` >= log2(nX) + 1, uniform
+__device__ __forceinline__ int coop_corank(const double* X, int nX, const double* Y, int nY, int g,
+                                           int steps)
+{
+    int lo = g - nY > 0 ? g - nY : 0, hi = g < nX ? g : nX;
+    for (int s = 0; s < steps; s++) {
+        const int mid = (lo + hi) >> 1;
+        const bool open = lo < hi;
+        const bool take = X[mid] <= Y[g - mid - 1];      // harmless garbage when !open
+        lo = (open && take) ? mid + 1 : lo;
+        hi = (open && !take) ? mid : hi;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int coop_log2_steps(int n)     // iterations that bisect [0, n] down to one
+{
+    return 32 - __clz(n > 0 ? n : 1);
+}
+
+// stage 1: elevation + azimuth -> one list of (t, elevation | azimuth << 16 after the event)
+__device__ __forceinline__ int coop_merge_ea(const CoopPlan& P, char* wbase, const CoopLists& L,
+                                             int lane, double*& tEA, int32_t*& sEA)
+{
+    tEA = reinterpret_cast<double*>(wbase + P.off_tEA);
+    sEA = reinterpret_cast<int32_t*>(wbase + P.off_sEA) + 1;
+    const int n = L.nE + L.nA;
+    const int c = (n + 31) >> 5;
+    const int g0 = lane * c;
+    int i = coop_corank(L.tE, L.nE, L.tA, L.nA, g0 < n ? g0 : n, coop_log2_steps(L.nE));
+    int j = (g0 < n ? g0 : n) - i;
+    int se = L.rE[i - 1], sa = L.rA[j - 1];
+    double xv = L.tE[i], yv = L.tA[j];
+    for (int g = g0; g < g0 + c; g++) {             // same trip count in every lane: no divergence
+        const bool tx = xv <= yv;
+        const double t = tx ? xv : yv;
+        const int reg = tx ? L.rE[i] : L.rA[j];
+        se = tx ? reg : se;
+        sa = tx ? sa : reg;
+        i += tx ? 1 : 0;
+        j += tx ? 0 : 1;
+        const double nv = tx ? L.tE[i] : L.tA[j];
+        xv = tx ? nv : xv;
+        yv = tx ? yv : nv;
+        if (g < n) { tEA[g] = t; sEA[g] = (se & 0xffff) | (sa << 16); }
+    }
+    if (lane == 0) { tEA[n] = SPHRT_INF; sEA[-1] = (L.rE[-1] & 0xffff) | ((int)L.rA[-1] << 16); }
+    __syncwarp();
+    return n;
+}
+
+// stage 2: radial + (elevation, azimuth); every merged event starts one segment that ends at the
+// next event: the reference's sort + forward-fill + diff (raytracer.py:131-151)
+template <bool kEvents, class Sink>
+__device__ __forceinline__ void coop_segments(const CoopLists& L, const double* tEA, const int32_t* sEA,
+                                              int nEA, int lane, Sink& sink)
+{
+    const int n = L.nR + nEA;
+    const int c = (n + 31) >> 5;
+    const int g0 = lane * c;
+    int i = coop_corank(L.tR, L.nR, tEA, nEA, g0 < n ? g0 : n, coop_log2_steps(L.nR));
+    int j = (g0 < n ? g0 : n) - i;
+    int sr = L.rR[i - 1], sea = sEA[j - 1];
+    double xv = L.tR[i], yv = tEA[j];
+    for (int g = g0; g < g0 + c; g++) {             // same trip count in every lane: no divergence
+        const bool tx = xv <= yv;
+        const double t = tx ? xv : yv;
+        const int reg = tx ? (int)L.rR[i] : sEA[j];
+        sr = tx ? reg : sr;
+        sea = tx ? sea : reg;
+        i += tx ? 1 : 0;
+        j += tx ? 0 : 1;
+        const double nv = tx ? L.tR[i] : tEA[j];
+        xv = tx ? nv : xv;
+        yv = tx ? yv : nv;
+        const double tn = fmin(xv, yv);
+        const double len = tn - t;
+        const int se = (int)(int16_t)(sea & 0xffff), sa = sea >> 16;
+        const bool ok = g < n && (sr | se | sa) >= 0 && len > 0 && tn < SPHRT_INF;
+        if constexpr (kEvents) { if (g < n) sink.event(g, sr, se, sa, ok ? len : 0.0); }
+        else { if (ok) sink.segment(sr, se, sa, len); }
+    }
+}
+
+}  // namespace sphrt

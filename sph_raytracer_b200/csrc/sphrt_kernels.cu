@@ -23,7 +23,10 @@
 #include <stdint.h>
 
 #include "../../include/sphrt.h"
-#include "sphrt_fast.cuh"
+#include <stdlib.h>
+#include <string.h>
+
+#include "sphrt_coop.cuh"
 
 using namespace sphrt;
 
@@ -141,7 +144,24 @@ struct ForwardOp {
         for (int c = 0; c < NCH; c++)
             if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
     }
-    __device__ __forceinline__ void block_end() const {}
+    // warp-cooperative walker: every lane holds a partial sum of the same ray
+    static constexpr bool kCoop = true, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t ray, Sink& s, int lane, int) const
+    {
+        s.flush();
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            double a = s.acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            s.acc[c] = a;
+        }
+        if (lane != 0) return;
+        if (m.rays_per_vol > 0) { out[ray] = (T)s.acc[0]; return; }
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
+    }
 };
 
 template <typename T, int NCH>
@@ -175,7 +195,8 @@ struct AdjointOp {
         return s;
     }
     __device__ __forceinline__ void end(int64_t, Sink&) const {}
-    __device__ __forceinline__ void block_end() const {}
+    static constexpr bool kCoop = true, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
 };
 
 // canonical segment bookkeeping shared by count / trace: consecutive identical voxels merge
@@ -195,7 +216,9 @@ struct CountOp {
         count[ray] = s.n;
         if (total != nullptr && s.n > 0) atomicAdd(total, (unsigned long long)s.n);
     }
-    __device__ __forceinline__ void block_end() const {}
+    // consecutive identical voxels merge: needs the segments in order, per-thread walker only
+    static constexpr bool kCoop = false, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
 };
 
 struct TraceOp {
@@ -221,7 +244,35 @@ struct TraceOp {
         return s;
     }
     __device__ __forceinline__ void end(int64_t ray, Sink& s) const { count[ray] = (int32_t)s.n; }
-    __device__ __forceinline__ void block_end() const {}
+    static constexpr bool kCoop = false, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
+};
+
+// Raw event export of the warp-cooperative walker (parity tests): every event of a ray at its
+// rank in the merged order, with the voxel that follows it and the length up to the next
+// event (0 where the reference zeroes the slot).  count stays untouched for rays that the
+// cooperative walker hands to the per-thread walker.
+struct EventTraceOp {
+    int32_t* vox; double* ev_len; int32_t* count; int64_t max_ev;
+    struct Sink {
+        int32_t* vox; double* len; int64_t max_ev;
+        __device__ __forceinline__ void segment(int, int, int, double) {}
+        __device__ __forceinline__ void event(int rank, int r, int e, int a, double l)
+        {
+            if (rank >= max_ev) return;
+            vox[3 * rank] = r; vox[3 * rank + 1] = e; vox[3 * rank + 2] = a; len[rank] = l;
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        return Sink{vox + 3 * ray * max_ev, ev_len + ray * max_ev, max_ev};
+    }
+    __device__ __forceinline__ void end(int64_t ray, Sink&) const { count[ray] = 0; }   // a miss
+    static constexpr bool kCoop = true, kEvents = true;
+    __device__ __forceinline__ void coop_end(int64_t ray, Sink&, int lane, int n_events) const
+    {
+        if (lane == 0) count[ray] = n_events;
+    }
 };
 
 // ---- the two passes ------------------------------------------------------------------------
@@ -259,6 +310,130 @@ walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem, uint
     typename Op::Sink sink = op.begin(mine ? i : 0);
     walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
     if (mine) op.end(i, sink);
+}
+
+// pass A', masked: the per-thread walker for the rays the cooperative walker handed over
+// (starts inside the grid or on a boundary, failed verification).  Persistent warps, one
+// 32-ray mask word at a time.
+template <class Op>
+__global__ void __launch_bounds__(kBlock, SPHRT_TRACKED_MIN_BLOCKS)
+walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem,
+                           const uint32_t* mask, int64_t n_words)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
+    double* qt = sm_tables + table_doubles_smem + threadIdx.x;
+    int* qr = reinterpret_cast<int*>(sm_tables + table_doubles_smem + 3 * kQueue * kBlock) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < n_words; w0 += warps * 32) {
+        // 32 mask words per warp and step; most are empty
+        const uint32_t mine = w0 + lane < n_words ? __ldg(mask + w0 + lane) : 0u;
+        uint32_t nonzero = __ballot_sync(0xffffffffu, mine != 0u);
+        for (; nonzero; nonzero &= nonzero - 1) {
+            const int src = __ffs(nonzero) - 1;
+            const uint32_t m = __shfl_sync(0xffffffffu, mine, src);
+            const int64_t i = ((w0 + src) << 5) + lane;
+            const bool active = (m >> lane) & 1u;
+            double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
+            RayConsts c;
+            if (active) { load_ray(kr, i, x, d); ray_setup(c, x, d); }
+            typename Op::Sink sink = op.begin(active ? i : 0);
+            walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+            if (active) op.end(i, sink);
+            __syncwarp();
+        }
+    }
+}
+
+// Warp-cooperative walker (sphrt_coop.cuh): persistent warps, 32 rays per tile; phase 0 plans
+// one ray per lane, phase 1 walks the tile's rays one after the other with all 32 lanes.
+constexpr int kCoopMaxWarps = 16;
+constexpr int kCoopRecDoubles = 7;
+
+template <class Op>
+__global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
+walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_mask,
+                 uint32_t* tracked_mask, unsigned long long* tile_counter, unsigned long long* stats)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    char* wbase = reinterpret_cast<char*>(sm_tables + P.table_doubles) + (size_t)warp * P.warp_bytes;
+    double* recd = reinterpret_cast<double*>(wbase + P.off_rec);
+    const int64_t n_tiles = (kr.n + 31) >> 5;
+    unsigned long long n_coop = 0, n_handed = 0;
+    for (;;) {
+        // tiles are handed out dynamically: their cost varies from nothing (misses) to ~1 ms
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(tile_counter, 1ull);
+        const int64_t tile = (int64_t)__shfl_sync(0xffffffffu, next, 0);
+        if (tile >= n_tiles) break;
+        // ---- phase 0: one lane per ray
+        const int64_t i = (tile << 5) + lane;
+        int cls = COOP_MISS;
+        int ri0 = 0, ri1 = 0, ri2 = 0, ri3 = 0, ri4 = 0, ri5 = 0;      // integer part of the record
+        if (i < kr.n) {
+            double x[3], d[3];
+            load_ray(kr, i, x, d);
+            RayConsts c;
+            ray_setup(c, x, d);
+            CoopRecord rec;
+            cls = coop_plan_ray(g, c, x, P, rec);
+            if (cls == COOP_RAY) {
+                recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
+                recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2; recd[5 * 32 + lane] = rec.nx2;
+                recd[6 * 32 + lane] = rec.t_turn;
+                ri0 = rec.imin | (rec.e_mid << 16);
+                ri1 = rec.e_first; ri2 = rec.e_count * rec.e_step;
+                ri3 = rec.a_first; ri4 = rec.a_count * rec.a_dir;
+                ri5 = (rec.se0 & 0xffff) | (rec.sa0 << 16);
+            }
+        }
+        if (cls == COOP_MISS && i < kr.n) {           // never enters the grid: empty result
+            typename Op::Sink none = op.begin(i);
+            op.end(i, none);
+        }
+        const uint32_t m_ray = __ballot_sync(0xffffffffu, cls == COOP_RAY);
+        const uint32_t m_listed = __ballot_sync(0xffffffffu, cls == COOP_LISTED);
+        uint32_t m_tracked = __ballot_sync(0xffffffffu, cls == COOP_TRACKED);
+        __syncwarp();
+        // ---- phase 1: 32 lanes per ray
+        for (uint32_t m = m_ray; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const int64_t ray = (tile << 5) + j;
+            CoopRecord rec;
+            rec.d0 = recd[0 * 32 + j]; rec.d1 = recd[1 * 32 + j]; rec.d2 = recd[2 * 32 + j];
+            rec.tc = recd[3 * 32 + j]; rec.dperp2 = recd[4 * 32 + j]; rec.nx2 = recd[5 * 32 + j];
+            rec.t_turn = recd[6 * 32 + j];
+            const int im = __shfl_sync(0xffffffffu, ri0, j);
+            rec.imin = im & 0xffff; rec.e_mid = im >> 16;
+            rec.e_first = __shfl_sync(0xffffffffu, ri1, j);
+            const int ec = __shfl_sync(0xffffffffu, ri2, j), ac = __shfl_sync(0xffffffffu, ri4, j);
+            const int stt = __shfl_sync(0xffffffffu, ri5, j);
+            rec.e_step = ec < 0 ? -1 : 1; rec.e_count = ec < 0 ? -ec : ec;
+            rec.a_first = __shfl_sync(0xffffffffu, ri3, j);
+            rec.a_dir = ac < 0 ? -1 : 1; rec.a_count = ac < 0 ? -ac : ac;
+            rec.se0 = (int)(int16_t)(stt & 0xffff); rec.sa0 = stt >> 16;
+            const double* xs = kr.starts + 3 * (ray / kr.rps);
+            const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
+            CoopLists L;
+            if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_tracked |= 1u << j; n_handed++; continue; }
+            typename Op::Sink sink = op.begin(ray);
+            double* tEA; int32_t* sEA;
+            const int nEA = coop_merge_ea(P, wbase, L, lane, tEA, sEA);
+            coop_segments<Op::kEvents>(L, tEA, sEA, nEA, lane, sink);
+            op.coop_end(ray, sink, lane, L.nR + L.nE + L.nA);
+            n_coop++;
+            __syncwarp();              // the lists are reused by the next ray
+        }
+        if (lane == 0) { listed_mask[tile] = m_listed; tracked_mask[tile] = m_tracked; }
+        if (stats != nullptr && lane == 0) {
+            atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));
+            atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
+        }
+    }
+    if (stats != nullptr && lane == 0) { atomicAdd(stats + 0, n_coop); atomicAdd(stats + 3, n_handed); }
 }
 
 // pass B: persistent warps walk the rays flagged by pass A from a heap-sorted list of all cone
@@ -350,6 +525,55 @@ ListPlan plan_lists(const sphrt_grid& g, int64_t n_rays)
 
 int64_t mask_bytes(int64_t n_rays) { return ((n_rays + 31) / 32 * 4 + 255) / 256 * 256; }
 
+// ---- warp-cooperative walker: shared-memory plan and selection -----------------------------------
+struct CoopLaunch { CoopPlan P; size_t smem; int64_t blocks; bool ok; };
+
+CoopLaunch plan_coop(const sphrt_grid& g, int64_t n_rays)
+{
+    CoopLaunch c;
+    CoopPlan& P = c.P;
+    P.capR = 2 * (g.nr + 1);
+    P.capE = g.ne + 12;
+    P.capA = g.na / 2 + 4;
+    int off = 0;
+    auto take = [&off](int bytes) { const int o = off; off += (bytes + 7) / 8 * 8; return o; };
+    P.off_tR = take((P.capR + 1) * 8);
+    P.off_tE = take((P.capE + 1) * 8);
+    P.off_tA = take((P.capA + 1) * 8);
+    P.off_rR = take((P.capR + 2) * 2);
+    P.off_rE = take((P.capE + 2) * 2);
+    P.off_rA = take((P.capA + 2) * 2);
+    // a chord's colatitude varies by less than pi and its azimuth by at most pi
+    P.capEA = g.ne + g.na / 2 + 16;
+    P.off_tEA = take((P.capEA + 1) * 8);
+    P.off_sEA = take((P.capEA + 2) * 4);
+    P.off_rec = take(32 * kCoopRecDoubles * 8);
+    P.warp_bytes = off;
+    P.table_doubles = (int)table_doubles(g);
+    const int64_t tables = table_doubles(g) * (int64_t)sizeof(double);
+    int64_t warps = (220 * 1024 - tables) / P.warp_bytes;
+    if (warps > kCoopMaxWarps) warps = kCoopMaxWarps;
+    c.ok = warps >= 4;
+    P.warps = (int)(warps > 0 ? warps : 1);
+    c.smem = (size_t)(tables + (int64_t)P.warps * P.warp_bytes);
+    const int64_t tiles = (n_rays + 31) / 32;
+    c.blocks = num_sms();
+    const int64_t want = (tiles + P.warps - 1) / P.warps;
+    if (c.blocks > want) c.blocks = want;
+    if (c.blocks < 1) c.blocks = 1;
+    return c;
+}
+
+// SPHRT_WALKER = auto (default) | coop | tracked : which walker takes the ordinary rays.
+// auto: the cooperative walker pays off once a ray meets a few hundred boundaries.
+bool want_coop(const sphrt_grid& g)
+{
+    const char* e = getenv("SPHRT_WALKER");
+    if (e != nullptr && strcmp(e, "coop") == 0) return true;
+    if (e != nullptr && strcmp(e, "tracked") == 0) return false;
+    return g.nr + g.ne + g.na >= 400;
+}
+
 int check_grid(const sphrt_grid* g)
 {
     if (g == nullptr) return SPHRT_EINVAL;
@@ -378,8 +602,27 @@ int cuda_status()
 }
 
 template <class Op>
+int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const uint32_t* mask,
+                  void* lists, size_t smem, const ListPlan& lp, cudaStream_t st)
+{
+    double* glist_t = nullptr;
+    int* glist_r = nullptr;
+    if (lp.global_lists) {
+        glist_t = (double*)lists;
+        glist_r = (int*)(glist_t + lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1));
+    }
+    if (lp.smem > 48 * 1024)
+        cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
+    walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
+        *grid, kr, op, mask, (kr.n + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r);
+    return cuda_status();
+}
+
+// scratch layout: [listed mask][tracked mask][global cone lists, if any]
+template <class Op>
 int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
-                  void* scratch, int64_t scratch_bytes, void* stream)
+                  void* scratch, int64_t scratch_bytes, void* stream, bool force_coop = false,
+                  unsigned long long* stats = nullptr)
 {
     if (rays->n_rays == 0) return SPHRT_OK;
     if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
@@ -388,27 +631,50 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
     const size_t smem_a = smem + kQueueBytes;
     const ListPlan lp = plan_lists(*grid, rays->n_rays);
+    uint32_t* mask = (uint32_t*)scratch;
+    uint32_t* mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
+    void* lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
+    const int64_t n_words = (rays->n_rays + 31) / 32;
+
+    if constexpr (Op::kCoop) {
+        const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
+        if (cl.ok && (force_coop || want_coop(*grid))) {
+            cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            unsigned long long* tile_counter = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
+            cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), st);
+            walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                *grid, kr, op, cl.P, mask, mask_tracked, tile_counter, stats);
+            int rc = cuda_status();
+            if (rc != SPHRT_OK) return rc;
+            if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
+            else {
+            if (smem_a > 48 * 1024)
+                cudaFuncSetAttribute(walk_tracked_masked_kernel<Op>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+            int64_t blocks_m = (int64_t)num_sms() * SPHRT_TRACKED_MIN_BLOCKS;
+            const int64_t want = (n_words + 32 * (kBlock / 32) - 1) / (32 * (kBlock / 32));
+            if (blocks_m > want) blocks_m = want;
+            if (blocks_m < 1) blocks_m = 1;
+            walk_tracked_masked_kernel<Op><<<(unsigned)blocks_m, kBlock, smem_a, st>>>(
+                *grid, kr, op, (int)(smem / sizeof(double)), mask_tracked, n_words);
+            rc = cuda_status();
+            if (rc != SPHRT_OK) return rc;
+            return launch_listed(grid, kr, op, mask, lists, smem, lp, st);
+            }
+        }
+    }
+    if constexpr (Op::kEvents) return SPHRT_ETOOBIG;
+    else {
     if (smem_a > 48 * 1024)
         cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-    if (lp.smem > 48 * 1024)
-        cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
     const int64_t blocks_a = (rays->n_rays + kBlock - 1) / kBlock;
     if (blocks_a > 0x7fffffffLL) return SPHRT_ETOOBIG;
-    uint32_t* mask = (uint32_t*)scratch;
     walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem_a, st>>>(*grid, kr, op,
                                                                        (int)(smem / sizeof(double)), mask);
     int rc = cuda_status();
     if (rc != SPHRT_OK) return rc;
-
-    double* glist_t = nullptr;
-    int* glist_r = nullptr;
-    if (lp.global_lists) {
-        glist_t = (double*)((char*)scratch + mask_bytes(rays->n_rays));
-        glist_r = (int*)(glist_t + lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1));
+    return launch_listed(grid, kr, op, mask, lists, smem, lp, st);
     }
-    walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
-        *grid, kr, op, mask, (rays->n_rays + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r);
-    return cuda_status();
 }
 
 template <template <typename, int> class OpT, typename T>
@@ -458,7 +724,7 @@ const char* sphrt_error_string(int code)
 int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
 {
     if (grid == nullptr || grid->ne < 1 || n_rays < 0) return 0;
-    int64_t bytes = mask_bytes(n_rays);
+    int64_t bytes = 2 * mask_bytes(n_rays) + 256;     // + tile counter of the cooperative walker
     const ListPlan lp = plan_lists(*grid, n_rays);
     if (lp.global_lists)
         bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
@@ -519,6 +785,18 @@ int sphrt_trace_segments(const sphrt_grid* grid, const sphrt_rays* rays, int64_t
     if (rays->n_rays > 0 && (!vox || !seg_len || !count)) return SPHRT_EINVAL;
     const TraceOp op{vox, seg_len, count, max_seg};
     return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_ev,
+                       int32_t* vox, double* ev_len, int32_t* count, unsigned long long* stats,
+                       void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (max_ev < 1) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!vox || !ev_len || !count)) return SPHRT_EINVAL;
+    const EventTraceOp op{vox, ev_len, count, max_ev};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream, true, stats);
 }
 
 int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)

@@ -325,6 +325,27 @@ class Operator:
         G = self._rays.shape
         return vox.reshape(G + (max_seg, 3)), lens.reshape(G + (max_seg,)), count.reshape(G)
 
+    def events(self, max_ev=None):
+        """Raw export of the warp-cooperative walker (parity tests): per ray every event in
+        merged order as ``vox (n, max_ev, 3)``, ``lens (n, max_ev)``, ``count (n)`` (-1 for
+        rays that walker hands to the per-thread walker) and the walker's statistics
+        ``(cooperative, listed, handed over, failed verification)``."""
+        t = self._tables
+        if max_ev is None:
+            max_ev = 2 * (t.nr + 1) + 2 * (t.ne + 1) + (t.na + 1) + 1
+        n = self._rays.n
+        vox = torch.full((n, max_ev, 3), -9, dtype=torch.int32, device=self._cdev)
+        lens = torch.zeros((n, max_ev), dtype=torch.float64, device=self._cdev)
+        count = torch.full((n,), -1, dtype=torch.int32, device=self._cdev)
+        stats = torch.zeros(4, dtype=torch.int64, device=self._cdev)
+        scratch = self._scratch()
+        with torch.cuda.device(self._cdev):
+            _cabi.check(self._lib.sphrt_trace_events(
+                self._tables.c, self._rays.c, max_ev, vox.data_ptr(), lens.data_ptr(),
+                count.data_ptr(), stats.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                self._stream()))
+        return vox, lens, count, tuple(stats.tolist())
+
     def _print_los(self, los):
         """debug=True: segment table of one line of sight (reference raytracer.py:175-225)."""
         vox, lens, count = self.segments()

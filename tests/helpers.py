@@ -80,3 +80,30 @@ def ragged_equal(c, count, vox, seg_len, mask=None, len_rtol=1e-9, len_atol=1e-1
         if not ok:
             bad.append(i)
     return len(idx), np.array(bad, dtype=np.int64)
+
+
+def canonical_from_events(vox, lens, count, max_seg):
+    """Canonical segments (non-zero length, consecutive identical voxels merged) from the raw
+    event export of the warp-cooperative walker.  Rays with count < 0 (not handled by that
+    walker) get count -1.  Returns (count, vox[n,max_seg,3], seg_len[n,max_seg])."""
+    n = len(count)
+    out_c = np.full(n, -1, dtype=np.int64)
+    out_v = np.full((n, max_seg, 3), -9, dtype=np.int32)
+    out_l = np.zeros((n, max_seg), dtype=np.float64)
+    for i in range(n):
+        k = int(count[i])
+        if k < 0:
+            continue
+        v, l = vox[i, :k], lens[i, :k]
+        keep = l > 0
+        v, l = v[keep], l[keep]
+        m = 0
+        for j in range(len(l)):
+            if m > 0 and np.array_equal(out_v[i, m - 1], v[j]):
+                out_l[i, m - 1] += l[j]
+                continue
+            if m < max_seg:
+                out_v[i, m] = v[j]; out_l[i, m] = l[j]
+            m += 1
+        out_c[i] = m
+    return out_c, out_v, out_l
