@@ -47,7 +47,7 @@ namespace sphrt {
 struct CoopPlan {
     int capR, capE, capA;     // event capacity of the three lists
     int off_tR, off_tE, off_tA;   // double arrays, capacity + 1 (sentinel)
-    int off_rR, off_rE, off_rA;   // int16 arrays, capacity + 1 (leading slot = state at entry)
+    int off_rE, off_rA;           // int16 arrays, capacity + 1 (leading slot = state at entry)
     int capEA, off_tEA, off_sEA;  // merged elevation + azimuth list: t, int32 packed state
     int off_rec;              // per-ray records: 7 double fields, [field][lane]
     int warp_bytes;
@@ -86,6 +86,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
                              near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
     if (bins[0] != g.nr || on_boundary) return COOP_TRACKED;      // starts inside / on a boundary
+    if (ray_has_snapped_aa(c, g.c2_sorted(), g.n_c2)) return COOP_TRACKED;   // see sphrt_walker.cuh
     if (c.dperp2 != c.dperp2) return COOP_MISS;                   // no radial root at all
     const double rN = g.r_b()[g.nr];
     const double argN = rN * rN - c.dperp2;
@@ -158,8 +159,16 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
 // ---- phase 1 ------------------------------------------------------------------------------------
 struct CoopLists {
     double *tR, *tE, *tA;     // ascending distances; [n] = +inf
-    int16_t *rR, *rE, *rA;    // region after the event; [-1] = state at entry
+    int16_t *rE, *rA;         // region after the event; [-1] = state at entry
     int nR, nE, nA;
+    int m, imin, nr;          // radial events: k < m first root of shell nr - k, else second root
+                              // of shell imin + k - m
+    // radial index after radial event k (k = -1: before the entry)
+    __device__ __forceinline__ int radial_region(int k) const
+    {
+        const int reg = k < m ? nr - 1 - k : imin + (k - m);
+        return reg == nr ? -1 : reg;
+    }
 };
 
 // Build the three sorted lists of ray `rec`.  Returns false if a structural assumption did not
@@ -182,7 +191,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
 
     // ---- radial: first roots of shells nr .. imin, then second roots of imin .. nr
     double* tR = reinterpret_cast<double*>(wbase + P.off_tR);
-    int16_t* rR = reinterpret_cast<int16_t*>(wbase + P.off_rR) + 1;
     const int m = g.nr - rec.imin + 1;
     const int nR = 2 * m;
     const double tang = 1e-17 * (1.0 + c.nx2);
@@ -194,13 +202,12 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
         const double arg = r2 - c.dperp2;
         const double t1c = sqrt(arg);
         const double tt = out ? c.tc + t1c : c.tc - t1c;
-        const int reg = out ? i : i - 1;
-        // tangent within rounding: the reference decides the region from the sign of d.p
+        // inward roots enter shell i - 1, outward roots shell i (CoopLists::radial_region); when
+        // tangent within rounding the reference decides from the sign of d.p: bail out
         if (!(arg >= tang + 1e-17 * r2)) bad = true;
         tR[k] = tt;
-        rR[k] = (int16_t)(reg == g.nr ? -1 : reg);
     }
-    if (lane == 0) { tR[nR] = SPHRT_INF; rR[-1] = -1; }
+    if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
     const double t_in = tR[0], t_out = tR[nR - 1];
 
@@ -276,9 +283,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     if (lane == 0) { tA[nA] = SPHRT_INF; rA[-1] = (int16_t)rec.sa0; }
     __syncwarp();
 
-    // ---- verify: ascending lists
-    for (int k = lane; k < nE - 1; k += 32) bad |= !(tE[k] <= tE[k + 1]);
-    for (int k = lane; k < nA - 1; k += 32) bad |= !(tA[k] <= tA[k + 1]);
+    // (the ascending order of both lists is verified while they are merged, coop_merge_ea)
     if (nE + nA > P.capEA) bad = true;
     if (__any_sync(SPHRT_FULL, bad)) return false;
     // glancing crossings leave the elevation index unchanged (region -2): forward-fill
@@ -287,8 +292,9 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
             for (int k = 0; k < nE; k++) if (rE[k] == -2) rE[k] = rE[k - 1];
         __syncwarp();
     }
-    L.tR = tR; L.tE = tE; L.tA = tA; L.rR = rR; L.rE = rE; L.rA = rA;
+    L.tR = tR; L.tE = tE; L.tA = tA; L.rE = rE; L.rA = rA;
     L.nR = nR; L.nE = nE; L.nA = nA;
+    L.m = m; L.imin = rec.imin; L.nr = g.nr;
     return true;
 }
 
@@ -317,7 +323,10 @@ __device__ __forceinline__ int coop_log2_steps(int n)     // iterations that bis
     return 32 - __clz(n > 0 ? n : 1);
 }
 
-// stage 1: elevation + azimuth -> one list of (t, elevation | azimuth << 16 after the event)
+// stage 1: elevation + azimuth -> one list of (t, elevation | azimuth << 16 after the event).
+// Returns the merged length, or -1 if one of the two lists is not ascending (every entry is
+// compared with its successor here: inside a lane's share when the successor is loaded, across
+// shares when a lane starts).
 __device__ __forceinline__ int coop_merge_ea(const CoopPlan& P, char* wbase, const CoopLists& L,
                                              int lane, double*& tEA, int32_t*& sEA)
 {
@@ -326,30 +335,40 @@ __device__ __forceinline__ int coop_merge_ea(const CoopPlan& P, char* wbase, con
     const int n = L.nE + L.nA;
     const int c = (n + 31) >> 5;
     const int g0 = lane * c;
-    int i = coop_corank(L.tE, L.nE, L.tA, L.nA, g0 < n ? g0 : n, coop_log2_steps(L.nE));
-    int j = (g0 < n ? g0 : n) - i;
-    int se = L.rE[i - 1], sa = L.rA[j - 1];
-    double xv = L.tE[i], yv = L.tA[j];
+    const int gs = g0 < n ? g0 : n;
+    const int i = coop_corank(L.tE, L.nE, L.tA, L.nA, gs, coop_log2_steps(L.nE));
+    const int j = gs - i;
+    const double* pE = L.tE + i;
+    const double* pA = L.tA + j;
+    const int16_t* qE = L.rE + i;
+    const int16_t* qA = L.rA + j;
+    int se = qE[-1], sa = qA[-1];
+    double xv = *pE, yv = *pA;
+    bool viol = (i > 0 && i < L.nE && pE[-1] > xv) || (j > 0 && j < L.nA && pA[-1] > yv);
+    bool tx = xv <= yv;
     for (int g = g0; g < g0 + c; g++) {             // same trip count in every lane: no divergence
-        const bool tx = xv <= yv;
         const double t = tx ? xv : yv;
-        const int reg = tx ? L.rE[i] : L.rA[j];
-        se = tx ? reg : se;
-        sa = tx ? sa : reg;
-        i += tx ? 1 : 0;
-        j += tx ? 0 : 1;
-        const double nv = tx ? L.tE[i] : L.tA[j];
-        xv = tx ? nv : xv;
-        yv = tx ? yv : nv;
-        if (g < n) { tEA[g] = t; sEA[g] = (se & 0xffff) | (sa << 16); }
+        const bool live = g < n;                    // beyond the end the heads are stale memory
+        if (tx) { se = *qE++; xv = *++pE; viol |= live && xv < t; }
+        else    { sa = *qA++; yv = *++pA; viol |= live && yv < t; }
+        tx = xv <= yv;
+        if (live) { tEA[g] = t; sEA[g] = (se & 0xffff) | (sa << 16); }
     }
     if (lane == 0) { tEA[n] = SPHRT_INF; sEA[-1] = (L.rE[-1] & 0xffff) | ((int)L.rA[-1] << 16); }
+    if (__any_sync(SPHRT_FULL, viol)) return -1;
     __syncwarp();
     return n;
 }
 
 // stage 2: radial + (elevation, azimuth); every merged event starts one segment that ends at the
-// next event: the reference's sort + forward-fill + diff (raytracer.py:131-151)
+// next event: the reference's sort + forward-fill + diff (raytracer.py:131-151).
+// The loop is unrolled by kCoopDepth so that a sink can keep that many gathers in flight
+// (Sink::segment_at<slot>): the volume sits in L2, a few hundred cycles away.
+#ifndef SPHRT_COOP_DEPTH
+#define SPHRT_COOP_DEPTH 1
+#endif
+constexpr int kCoopDepth = SPHRT_COOP_DEPTH;      // 1, 2 or 4
+
 template <bool kEvents, class Sink>
 __device__ __forceinline__ void coop_segments(const CoopLists& L, const double* tEA, const int32_t* sEA,
                                               int nEA, int lane, Sink& sink)
@@ -357,28 +376,44 @@ __device__ __forceinline__ void coop_segments(const CoopLists& L, const double* 
     const int n = L.nR + nEA;
     const int c = (n + 31) >> 5;
     const int g0 = lane * c;
-    int i = coop_corank(L.tR, L.nR, tEA, nEA, g0 < n ? g0 : n, coop_log2_steps(L.nR));
-    int j = (g0 < n ? g0 : n) - i;
-    int sr = L.rR[i - 1], sea = sEA[j - 1];
-    double xv = L.tR[i], yv = tEA[j];
-    for (int g = g0; g < g0 + c; g++) {             // same trip count in every lane: no divergence
-        const bool tx = xv <= yv;
-        const double t = tx ? xv : yv;
-        const int reg = tx ? (int)L.rR[i] : sEA[j];
-        sr = tx ? reg : sr;
-        sea = tx ? sea : reg;
-        i += tx ? 1 : 0;
-        j += tx ? 0 : 1;
-        const double nv = tx ? L.tR[i] : tEA[j];
-        xv = tx ? nv : xv;
-        yv = tx ? yv : nv;
-        const double tn = fmin(xv, yv);
-        const double len = tn - t;
-        const int se = (int)(int16_t)(sea & 0xffff), sa = sea >> 16;
-        const bool ok = g < n && (sr | se | sa) >= 0 && len > 0 && tn < SPHRT_INF;
-        if constexpr (kEvents) { if (g < n) sink.event(g, sr, se, sa, ok ? len : 0.0); }
-        else { if (ok) sink.segment(sr, se, sa, len); }
+    const int gs = g0 < n ? g0 : n;
+    int i = coop_corank(L.tR, L.nR, tEA, nEA, gs, coop_log2_steps(L.nR));
+    const int j = gs - i;
+    const double* pR = L.tR + i;
+    const double* pE = tEA + j;
+    const int32_t* qE = sEA + j;
+    int sr = L.radial_region(i - 1), sea = qE[-1];
+    double xv = *pR, yv = *pE;
+    bool tx = xv <= yv;
+    double t = tx ? xv : yv;
+    int g = g0;
+    // one merge step + one segment; the trip count is the same in every lane (no divergence)
+#define SPHRT_COOP_STEP(SLOT)                                                                     \
+    {                                                                                             \
+        if (tx) { sr = L.radial_region(i); i++; xv = *++pR; }                                     \
+        else    { sea = *qE++; yv = *++pE; }                                                      \
+        tx = xv <= yv;                                                                            \
+        const double tn = tx ? xv : yv;                                                           \
+        const double len = tn - t;                                                                \
+        /* after the exit event the radial index is -1: the +inf sentinel never yields a length */\
+        const bool ok = g < n && (sr | sea) >= 0 && (sea & 0x8000) == 0 && len > 0;               \
+        if constexpr (kEvents) {                                                                  \
+            if (g < n) sink.event(g, sr, (int)(int16_t)(sea & 0xffff), sea >> 16,                 \
+                                  ok && tn < SPHRT_INF ? len : 0.0);                              \
+        } else {                                                                                  \
+            sink.template segment_at<SLOT>(ok, sr, sea & 0xffff, sea >> 16, len);                 \
+        }                                                                                         \
+        t = tn; g++;                                                                              \
     }
+    const int g_end = g0 + c;
+    while (g + kCoopDepth <= g_end) {
+        SPHRT_COOP_STEP(0)
+        if constexpr (kCoopDepth > 1) SPHRT_COOP_STEP(1)
+        if constexpr (kCoopDepth > 2) { SPHRT_COOP_STEP(2) SPHRT_COOP_STEP(3) }
+    }
+    if constexpr (kCoopDepth > 1) { if (g < g_end) SPHRT_COOP_STEP(0) }
+    if constexpr (kCoopDepth > 2) { if (g < g_end) SPHRT_COOP_STEP(1) if (g < g_end) SPHRT_COOP_STEP(2) }
+#undef SPHRT_COOP_STEP
 }
 
 }  // namespace sphrt

@@ -249,10 +249,11 @@ SPHRT_HD void walk_ray_fast(const GridView& g, const RayConsts& c, const double 
             else { qR.push(SPHRT_INF, -2); }
             // A start that sits ON a cone or half-plane makes the reference lose or keep the
             // t ~ 0 crossing by rounding (e.g. single_vantage.py: pos (5,0,0) lies on the
-            // equator cone and on the plane a = 0); replay from t = 0 then.
+            // equator cone and on the plane a = 0); replay from t = 0 then.  Likewise when a
+            // cone's quadratic is snapped to a linear one (ray_has_snapped_aa).
             const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
                                      near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
-            if (bins[0] == g.nr && has_r && !on_boundary) {
+            if (bins[0] == g.nr && has_r && !on_boundary && !ray_has_snapped_aa(c, g.c2_sorted(), g.n_c2)) {
                 // starts outside the outermost shell: jump to the entry point.  Until then
                 // r = -1 and every length is zero; the elevation / azimuth state at entry
                 // is the bin of the entry point.

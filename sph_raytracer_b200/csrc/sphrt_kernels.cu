@@ -111,17 +111,37 @@ struct ForwardOp {
         const T* vol; int nvox; int ne, na; int nch;
         double acc[NCH], plen;
         T pval[NCH];
+        // cooperative walker: kCoopDepth gathers in flight per lane (slot k is consumed when the
+        // k-th next segment arrives); one channel only, wider batches take segment()
+        T rval[kCoopDepth]; double rlen[kCoopDepth];
+        template <int SLOT>
+        __device__ __forceinline__ void segment_at(bool ok, int r, int e, int a, double len)
+        {
+            if constexpr (NCH == 1) {
+                acc[0] = fma_rn((double)rval[SLOT], rlen[SLOT], acc[0]);
+                const int idx = ok ? (r * ne + e) * na + a : 0;
+                rval[SLOT] = __ldg(vol + idx);
+                rlen[SLOT] = ok ? len : 0.0;
+            } else {
+                if (ok) segment(r, e, a, len);
+            }
+        }
         __device__ __forceinline__ void flush()
         {
 #pragma unroll
             for (int c = 0; c < NCH; c++) acc[c] = fma_rn((double)pval[c], plen, acc[c]);
+            if constexpr (NCH == 1) {
+#pragma unroll
+                for (int k = 0; k < kCoopDepth; k++) acc[0] = fma_rn((double)rval[k], rlen[k], acc[0]);
+            }
         }
         __device__ __forceinline__ void segment(int r, int e, int a, double len)
         {
             const int idx = (r * ne + e) * na + a;
             flush();
 #pragma unroll
-            for (int c = 0; c < NCH; c++) pval[c] = c < nch ? __ldg(vol + (size_t)c * nvox + idx) : T(0);
+            for (int c = 0; c < NCH; c++)
+                pval[c] = (NCH == 1 || c < nch) ? __ldg(vol + (size_t)c * nvox + idx) : T(0);
             plen = len;
         }
     };
@@ -134,6 +154,8 @@ struct ForwardOp {
         s.plen = 0.0;
 #pragma unroll
         for (int c = 0; c < NCH; c++) { s.acc[c] = 0.0; s.pval[c] = T(0); }
+#pragma unroll
+        for (int k = 0; k < kCoopDepth; k++) { s.rval[k] = T(0); s.rlen[k] = 0.0; }
         return s;
     }
     __device__ __forceinline__ void end(int64_t ray, Sink& s) const
@@ -170,12 +192,17 @@ struct AdjointOp {
     struct Sink {
         T* vol; int nvox; int ne, na; int nch;
         double w[NCH];
+        template <int SLOT>
+        __device__ __forceinline__ void segment_at(bool ok, int r, int e, int a, double len)
+        {
+            if (ok) segment(r, e, a, len);
+        }
         __device__ __forceinline__ void segment(int r, int e, int a, double len)
         {
             const int idx = (r * ne + e) * na + a;
 #pragma unroll
             for (int c = 0; c < NCH; c++)
-                if (c < nch && w[c] != 0.0) atomicAdd(vol + (size_t)c * nvox + idx, (T)(w[c] * len));
+                if ((NCH == 1 || c < nch) && w[c] != 0.0) atomicAdd(vol + (size_t)c * nvox + idx, (T)(w[c] * len));
         }
     };
     __device__ __forceinline__ Sink begin(int64_t ray) const
@@ -257,6 +284,8 @@ struct EventTraceOp {
     struct Sink {
         int32_t* vox; double* len; int64_t max_ev;
         __device__ __forceinline__ void segment(int, int, int, double) {}
+        template <int SLOT>
+        __device__ __forceinline__ void segment_at(bool, int, int, int, double) {}
         __device__ __forceinline__ void event(int rank, int r, int e, int a, double l)
         {
             if (rank >= max_ev) return;
@@ -419,9 +448,10 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
             const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
             CoopLists L;
             if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_tracked |= 1u << j; n_handed++; continue; }
-            typename Op::Sink sink = op.begin(ray);
             double* tEA; int32_t* sEA;
             const int nEA = coop_merge_ea(P, wbase, L, lane, tEA, sEA);
+            if (nEA < 0) { m_tracked |= 1u << j; n_handed++; continue; }     // a list out of order
+            typename Op::Sink sink = op.begin(ray);
             coop_segments<Op::kEvents>(L, tEA, sEA, nEA, lane, sink);
             op.coop_end(ray, sink, lane, L.nR + L.nE + L.nA);
             n_coop++;
@@ -540,7 +570,6 @@ CoopLaunch plan_coop(const sphrt_grid& g, int64_t n_rays)
     P.off_tR = take((P.capR + 1) * 8);
     P.off_tE = take((P.capE + 1) * 8);
     P.off_tA = take((P.capA + 1) * 8);
-    P.off_rR = take((P.capR + 2) * 2);
     P.off_rE = take((P.capE + 2) * 2);
     P.off_rA = take((P.capA + 2) * 2);
     // a chord's colatitude varies by less than pi and its azimuth by at most pi

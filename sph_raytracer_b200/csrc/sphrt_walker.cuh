@@ -341,6 +341,20 @@ SPHRT_HD bool ray_needs_cone_list(const RayConsts& c, const double* c2_sorted, i
     return false;
 }
 
+// The snap |aa| < tau (:376) turns a cone's quadratic into the linear equation bb t + cc = 0 when
+// the ray's inclination matches the cone's (dz^2 ~ cos^2 e_i).  For the plane-like cone
+// e = pi/2 that root lies at HALF the distance of the real crossing (the quadratic there is the
+// perfect square (dz t + xz)^2), so for nearly horizontal rays the reference changes the
+// elevation index somewhere else than the geometry does.  The walkers reproduce that by
+// evaluating the same formulas, but such rays must not take shortcuts that rely on the geometric
+// elevation bin of a point (the fast-forward to the entry point).
+SPHRT_HD bool ray_has_snapped_aa(const RayConsts& c, const double* c2_sorted, int n_c2)
+{
+    const double w = SPHRT_TAU * 1.0001;
+    if (!(c.dz2 >= w + 1e-9)) return true;         // cones within tau of pi/2 (not in the table)
+    return table_hits(c2_sorted, n_c2, c.dz2 - w, c.dz2 + w);
+}
+
 // Per-thread scratch for the sorted cone-root list (element k at [k * stride]).
 struct ConeList {
     double* t; int* r; int64_t stride; int capacity;
