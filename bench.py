@@ -289,6 +289,17 @@ def run_gpu(args):
         peak, how = measured_peak()
         seg_r, rays_r = float(n_seg), float(n_rays)           # rank 0's launch
         dom = "adjoint" if t_adj >= t_fwd else "forward"
+        coop = op.walker() == "cooperative"
+        kname = "walk_coop_kernel" if coop else "walk_tracked_kernel"
+        # DRAM bytes per ray of that kernel from the committed ncu --set full capture
+        # (profiles/: a 524 288-ray launch of this workload), scaled to this launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)[kname][dom]
+            traffic = tr["dram_bytes"] / tr["rays"] * rays_r if args.workload == "c5" else None
+        except Exception:
+            pass
         per = ADJ_BYTES if dom == "adjoint" else FWD_BYTES
         alg_bytes = per[0] * seg_r + per[1] * rays_r + per[2] * nvox
         t_dom = max(t_adj, t_fwd)
@@ -306,13 +317,16 @@ def run_gpu(args):
                               "no explicit flush"),
             "rays_per_s": 2 * tot_rays / (ms / 1e3),
             "kernel_ms": {"forward": t_fwd, "adjoint": t_adj},
-            "roofline": {"bound": "hbm", "kernel": f"walk_tracked_kernel<{dom}>",
+            "roofline": {"bound": "hbm", "kernel": f"{kname}<{dom}>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": how,
+                         "traffic": traffic, "peak_source": how,
+                         "traffic_source": "ncu dram__bytes_read+write of a 524288-ray launch, scaled per ray",
                          "algorithmic_bytes": f"{per[0]} B/segment + {per[1]} B/ray + {per[2]} B/voxel"},
             "e2e": {"value": 2 * tot_seg / (e2e_step / 1e3), "unit": "ray-segments/s",
                     "ms_per_step": e2e_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": 4 * args.steps,
+            # per pass: ordinary-ray walker + sorted-cone-list pass (+ masked per-thread pass)
+            "gpu_launches": (6 if coop else 4) * args.steps,
+            "walker": op.walker(),
             "clocks": clocks,
             "peak_memory_gb": peak_bytes / 1e9,
             "operator_build_s": t_build,

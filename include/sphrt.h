@@ -122,6 +122,12 @@ int sphrt_trace_events(const sphrt_grid *grid, const sphrt_rays *rays, int64_t m
                        unsigned long long *stats,
                        void *scratch, int64_t scratch_bytes, void *stream);
 
+/* Which kernel walks the ordinary rays of this grid in sphrt_forward / sphrt_adjoint:
+ * 1 = warp-cooperative walker (csrc/sphrt_coop.cuh; large grids), 0 = per-thread walker.
+ * Both produce the same segments; the choice (grid size, overridable with the environment
+ * variable SPHRT_WALKER = auto | coop | tracked) only affects speed.  Negative: error code. */
+int sphrt_walker_kind(const sphrt_grid *grid, int64_t n_rays);
+
 /* find_starts (raytracer.py:605-644): voxel of n points; out is (3, n) int32 with -1
  * for "outside" exactly like the reference. */
 int sphrt_find_starts(const sphrt_grid *grid, int64_t n, const double *xs, int32_t *out,

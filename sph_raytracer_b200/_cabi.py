@@ -14,7 +14,7 @@ F32, F64 = 0, 1
 
 EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphrt_scratch_bytes",
            "sphrt_forward", "sphrt_adjoint", "sphrt_count_segments", "sphrt_trace_segments",
-           "sphrt_find_starts", "sphrt_trace_events")
+           "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind")
 
 
 class Grid(ctypes.Structure):
@@ -69,6 +69,8 @@ def load(path=None):
     lib.sphrt_trace_events.restype = c_int
     lib.sphrt_trace_events.argtypes = [P(Grid), P(Rays), c_int64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int64, c_void_p]
+    lib.sphrt_walker_kind.restype = c_int
+    lib.sphrt_walker_kind.argtypes = [P(Grid), c_int64]
     lib.sphrt_find_starts.restype = c_int
     lib.sphrt_find_starts.argtypes = [P(Grid), c_int64, c_void_p, c_void_p, c_void_p]
     _lib = lib

@@ -49,7 +49,7 @@ struct CoopPlan {
     int off_tR, off_tE, off_tA;   // double arrays, capacity + 1 (sentinel)
     int off_rE, off_rA;           // int16 arrays, capacity + 1 (leading slot = state at entry)
     int capEA, off_tEA, off_sEA;  // merged elevation + azimuth list: t, int32 packed state
-    int off_rec;              // per-ray records: 7 double fields, [field][lane]
+    int off_rec;              // per-ray records: 6 double fields, [field][lane]
     int warp_bytes;
     int warps;                // warps per block
     int table_doubles;
@@ -58,7 +58,7 @@ struct CoopPlan {
 enum { COOP_MISS = 0, COOP_RAY = 1, COOP_LISTED = 2, COOP_TRACKED = 3 };
 
 struct CoopRecord {           // what phase 1 needs to know about a ray (warp-uniform there)
-    double d0, d1, d2, tc, dperp2, nx2, t_turn;
+    double d0, d1, d2, tc, dperp2, t_turn;
     int imin;                 // innermost shell reached
     int e_first, e_count, e_step;     // cone candidates e_first + k * e_step, k < e_count
     int e_mid;                // slot of the elevation buffer where the two runs meet
@@ -104,7 +104,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     }
     rec.imin = lo;
     rec.d0 = c.d0; rec.d1 = c.d1; rec.d2 = c.d2;
-    rec.tc = c.tc; rec.dperp2 = c.dperp2; rec.nx2 = c.nx2;
+    rec.tc = c.tc; rec.dperp2 = c.dperp2;
 
     // entry / exit points and the voxel state at entry (as walk_ray_fast's fast-forward)
     const double p[3] = {c.d0 * t_in + c.x0, c.d1 * t_in + c.x1, c.d2 * t_in + c.x2};
@@ -180,7 +180,8 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     RayConsts c;
     c.x0 = x[0]; c.x1 = x[1]; c.x2 = x[2];
     c.d0 = rec.d0; c.d1 = rec.d1; c.d2 = rec.d2;
-    c.tc = rec.tc; c.dperp2 = rec.dperp2; c.nx2 = rec.nx2;
+    c.tc = rec.tc; c.dperp2 = rec.dperp2;
+    { const double nx = norm3(c.x0, c.x1, c.x2); c.nx2 = nx * nx; }      // as ray_setup
     c.dz2 = c.d2 * c.d2;
     c.dzxz = c.d2 * c.x2;
     c.dx = dot3(c.d0, c.d1, c.d2, c.x0, c.x1, c.x2);
@@ -194,6 +195,25 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     const int m = g.nr - rec.imin + 1;
     const int nR = 2 * m;
     const double tang = 1e-17 * (1.0 + c.nx2);
+#ifdef SPHRT_COOP_UNROLL_R
+    // two shells per lane and step: two independent sqrt chains in flight
+    for (int k = lane; k < nR; k += 64) {
+        const int k2 = k + 32;
+        const bool out = k >= m, out2 = k2 >= m;
+        const int i = out ? rec.imin + (k - m) : g.nr - k;
+        int i2 = out2 ? rec.imin + (k2 - m) : g.nr - k2;
+        if (k2 >= nR) i2 = g.nr;
+        const double r = g.r_b()[i], rr = g.r_b()[i2];
+        const double r2 = r * r, rr2 = rr * rr;
+        const double arg = r2 - c.dperp2, arg2 = rr2 - c.dperp2;
+        const double t1c = sqrt(arg), t2c = sqrt(arg2);
+        const double tt = out ? c.tc + t1c : c.tc - t1c;
+        const double tt2 = out2 ? c.tc + t2c : c.tc - t2c;
+        if (!(arg >= tang + 1e-17 * r2) || !(arg2 >= tang + 1e-17 * rr2)) bad = true;
+        tR[k] = tt;
+        if (k2 < nR) tR[k2] = tt2;
+    }
+#else
     for (int k = lane; k < nR; k += 32) {
         const bool out = k >= m;
         const int i = out ? rec.imin + (k - m) : g.nr - k;
@@ -207,6 +227,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
         if (!(arg >= tang + 1e-17 * r2)) bad = true;
         tR[k] = tt;
     }
+#endif
     if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
     const double t_in = tR[0], t_out = tR[nR - 1];

@@ -83,7 +83,12 @@ __device__ __forceinline__ void load_ray(const KRays& kr, int64_t i, double x[3]
     const double* xs = kr.starts + 3 * (i / kr.rps);
     const double* ds = kr.dirs + 3 * (i / kr.rpd);
     x[0] = __ldg(xs); x[1] = __ldg(xs + 1); x[2] = __ldg(xs + 2);
+#ifdef SPHRT_STREAM_RAYS
+    // directions are read once per pass: stream them past the L2-resident volume
+    d[0] = __ldcs(ds); d[1] = __ldcs(ds + 1); d[2] = __ldcs(ds + 2);
+#else
     d[0] = __ldg(ds); d[1] = __ldg(ds + 1); d[2] = __ldg(ds + 2);
+#endif
 }
 
 // ---- per-ray operations ------------------------------------------------------------------
@@ -378,7 +383,7 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 // Warp-cooperative walker (sphrt_coop.cuh): persistent warps, 32 rays per tile; phase 0 plans
 // one ray per lane, phase 1 walks the tile's rays one after the other with all 32 lanes.
 constexpr int kCoopMaxWarps = 16;
-constexpr int kCoopRecDoubles = 7;
+constexpr int kCoopRecDoubles = 6;
 
 template <class Op>
 __global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
@@ -411,8 +416,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
             cls = coop_plan_ray(g, c, x, P, rec);
             if (cls == COOP_RAY) {
                 recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
-                recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2; recd[5 * 32 + lane] = rec.nx2;
-                recd[6 * 32 + lane] = rec.t_turn;
+                recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
+                recd[5 * 32 + lane] = rec.t_turn;
                 ri0 = rec.imin | (rec.e_mid << 16);
                 ri1 = rec.e_first; ri2 = rec.e_count * rec.e_step;
                 ri3 = rec.a_first; ri4 = rec.a_count * rec.a_dir;
@@ -433,8 +438,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
             const int64_t ray = (tile << 5) + j;
             CoopRecord rec;
             rec.d0 = recd[0 * 32 + j]; rec.d1 = recd[1 * 32 + j]; rec.d2 = recd[2 * 32 + j];
-            rec.tc = recd[3 * 32 + j]; rec.dperp2 = recd[4 * 32 + j]; rec.nx2 = recd[5 * 32 + j];
-            rec.t_turn = recd[6 * 32 + j];
+            rec.tc = recd[3 * 32 + j]; rec.dperp2 = recd[4 * 32 + j];
+            rec.t_turn = recd[5 * 32 + j];
             const int im = __shfl_sync(0xffffffffu, ri0, j);
             rec.imin = im & 0xffff; rec.e_mid = im >> 16;
             rec.e_first = __shfl_sync(0xffffffffu, ri1, j);
@@ -826,6 +831,12 @@ int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t m
     if (rays->n_rays > 0 && (!vox || !ev_len || !count)) return SPHRT_EINVAL;
     const EventTraceOp op{vox, ev_len, count, max_ev};
     return launch_passes(grid, rays, op, scratch, scratch_bytes, stream, true, stats);
+}
+
+int sphrt_walker_kind(const sphrt_grid* grid, int64_t n_rays)
+{
+    if (check_grid(grid) != SPHRT_OK) return SPHRT_EINVAL;
+    return (plan_coop(*grid, n_rays).ok && want_coop(*grid)) ? 1 : 0;
 }
 
 int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)

@@ -325,6 +325,12 @@ class Operator:
         G = self._rays.shape
         return vox.reshape(G + (max_seg, 3)), lens.reshape(G + (max_seg,)), count.reshape(G)
 
+    def walker(self):
+        """'cooperative' or 'per-thread': the kernel that walks this operator's ordinary rays."""
+        kind = int(self._lib.sphrt_walker_kind(self._tables.c, self._rays.n))
+        _cabi.check(min(kind, 0))
+        return "cooperative" if kind == 1 else "per-thread"
+
     def events(self, max_ev=None):
         """Raw export of the warp-cooperative walker (parity tests): per ray every event in
         merged order as ``vox (n, max_ev, 3)``, ``lens (n, max_ev)``, ``count (n)`` (-1 for
