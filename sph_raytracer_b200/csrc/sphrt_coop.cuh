@@ -66,12 +66,26 @@ struct CoopRecord {           // what phase 1 needs to know about a ray (warp-un
     int se0, sa0;             // elevation / azimuth state at the entry point
 };
 
-__device__ __forceinline__ int coop_bin_e(const GridView& g, const double p[3], double* e_out)
+// Phase 0 runs once per 32 rays; its big library routines are kept out of line so that the
+// kernel's hot loops stay close together in the instruction cache.
+#ifdef SPHRT_COOP_NOINLINE
+#define SPHRT_COLD __device__ __noinline__
+#else
+#define SPHRT_COLD __device__ __forceinline__
+#endif
+SPHRT_COLD double coop_atan2(double y, double x) { return atan2(y, x); }
+
+// geometric bins and reference states of a point, as start_voxel()
+SPHRT_COLD void coop_locate_point(const GridView& g, double p0, double p1, double p2, int bins[3],
+                                  int st[3], double sph[3])
 {
-    const double e = atan2(sqrt(p[0] * p[0] + p[1] * p[1]), p[2]);
-    int st;
-    *e_out = e;
-    return locate(g.e_b(), g.ne, e, &st);
+    const double xy = p0 * p0 + p1 * p1;
+    sph[0] = sqrt(xy + p2 * p2);
+    sph[1] = coop_atan2(sqrt(xy), p2);
+    sph[2] = coop_atan2(p1, p0);
+    bins[0] = locate(g.r_b(), g.nr, sph[0], &st[0]);
+    bins[1] = locate(g.e_b(), g.ne, sph[1], &st[1]);
+    bins[2] = locate(g.a_b(), g.na, sph[2], &st[2]);
 }
 
 // ---- phase 0: classify one ray and plan its candidate ranges ---------------------------------
@@ -82,7 +96,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     if (!g.wrap) return COOP_TRACKED;             // partial azimuth range: gap sector logic
     int bins[3], st[3];
     double sph[3];
-    start_voxel(g, x, bins, st, sph);
+    coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
     const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
                              near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
     if (bins[0] != g.nr || on_boundary) return COOP_TRACKED;      // starts inside / on a boundary
@@ -109,15 +123,13 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     // entry / exit points and the voxel state at entry (as walk_ray_fast's fast-forward)
     const double p[3] = {c.d0 * t_in + c.x0, c.d1 * t_in + c.x1, c.d2 * t_in + c.x2};
     const double q[3] = {c.d0 * t_out + c.x0, c.d1 * t_out + c.x1, c.d2 * t_out + c.x2};
-    int pb[3], ps[3];
-    double psph[3];
-    start_voxel(g, p, pb, ps, psph);
+    int pb[3], ps[3], qb[3], qs[3];
+    double psph[3], qsph[3];
+    coop_locate_point(g, p[0], p[1], p[2], pb, ps, psph);
     rec.se0 = ps[1]; rec.sa0 = ps[2];
-    double qe;
-    const int qb_e = coop_bin_e(g, q, &qe);
-    const double qa = atan2(q[1], q[0]);
-    int qs_a;
-    const int qb_a = locate(g.a_b(), g.na, qa, &qs_a);
+    coop_locate_point(g, q[0], q[1], q[2], qb, qs, qsph);
+    const double qe = qsph[1];
+    const int qb_e = qb[1], qb_a = qb[2];
 
     // ---- elevation: colatitude is unimodal along the chord; turning point at t*
     const double den = c.d2 * c.dx - c.x2;
@@ -126,8 +138,11 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     double t_turn = -SPHRT_INF;
     if (tstar > t_in && tstar < t_out) {
         const double m[3] = {c.d0 * tstar + c.x0, c.d1 * tstar + c.x1, c.d2 * tstar + c.x2};
-        double me;
-        const int mb = coop_bin_e(g, m, &me);
+        int mbins[3], mst[3];
+        double msph[3];
+        coop_locate_point(g, m[0], m[1], m[2], mbins, mst, msph);
+        const double me = msph[1];
+        const int mb = mbins[1];
         t_turn = tstar;
         const int top = pb[1] > qb_e ? pb[1] : qb_e, bot = pb[1] < qb_e ? pb[1] : qb_e;
         if (me < psph[1]) { step = +1; first = mb; count = top + 2 - mb; }        // dips towards +Z

@@ -346,38 +346,82 @@ walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem, uint
     if (mine) op.end(i, sink);
 }
 
+// Flagged-ray iterator of the fallback passes.  Flagged rays are rare (about 1 %) and scattered,
+// so walking them where they sit in their 32-ray mask word leaves most lanes idle for the whole
+// (long, serial) walk.  Instead a warp scans mask words in chunks handed out by an atomic
+// counter, compacts the flagged ray indices into a small shared-memory queue and calls
+// `walk(ray, active)` with 32 of them at a time; the remainder is flushed at the end.
+// Flagged rays come in dense runs (whole detector rows near the equatorial plane), so the 32
+// words of one hand-out are taken from 32 far-apart, mutually rotated places of the mask: every
+// hand-out then holds about the same number of flagged rays.
+constexpr int kChunkWords = 32;       // mask words (1024 rays) per hand-out
+constexpr int kFlagQueue = 64;        // ray indices buffered per warp
+
+template <class Walk>
+__device__ __forceinline__ void for_each_flagged(const uint32_t* mask, int64_t n_words,
+                                                 unsigned long long* chunk_counter,
+                                                 int64_t* queue /* this warp's kFlagQueue slots */,
+                                                 Walk walk)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int head = 0, count = 0;          // ring buffer state, warp-uniform
+    const int64_t n_chunks = (n_words + kChunkWords - 1) / kChunkWords;
+    for (;;) {
+        unsigned long long next = 0;
+        if (lane == 0) next = atomicAdd(chunk_counter, 1ull);
+        const int64_t chunk = (int64_t)__shfl_sync(0xffffffffu, next, 0);
+        if (chunk >= n_chunks) break;
+        // lane k reads word k * n_chunks + (chunk + k * R) mod n_chunks: a bijection onto the mask
+        const int64_t my_word = lane * n_chunks + (chunk + lane * (int64_t)0x9E3779B1u) % n_chunks;
+        const uint32_t mine = my_word < n_words ? __ldg(mask + my_word) : 0u;
+        uint32_t nonzero = __ballot_sync(0xffffffffu, mine != 0u);
+        for (; nonzero; nonzero &= nonzero - 1) {
+            const int src = __ffs(nonzero) - 1;
+            const uint32_t m = __shfl_sync(0xffffffffu, mine, src);
+            const int64_t word = __shfl_sync(0xffffffffu, my_word, src);
+            if ((m >> lane) & 1u)
+                queue[(head + count + __popc(m & lt_mask)) & (kFlagQueue - 1)] = (word << 5) + lane;
+            count += __popc(m);
+            __syncwarp();
+            if (count >= 32) {
+                const int64_t ray = queue[(head + lane) & (kFlagQueue - 1)];
+                head = (head + 32) & (kFlagQueue - 1); count -= 32;
+                __syncwarp();
+                walk(ray, true);
+                __syncwarp();
+            }
+        }
+    }
+    if (count > 0) {
+        const bool active = lane < count;
+        const int64_t ray = active ? queue[(head + lane) & (kFlagQueue - 1)] : 0;
+        walk(ray, active);
+    }
+}
+
 // pass A', masked: the per-thread walker for the rays the cooperative walker handed over
 // (starts inside the grid or on a boundary, failed verification).  Persistent warps, one
 // 32-ray mask word at a time.
 template <class Op>
 __global__ void __launch_bounds__(kBlock, SPHRT_TRACKED_MIN_BLOCKS)
 walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem,
-                           const uint32_t* mask, int64_t n_words)
+                           const uint32_t* mask, int64_t n_words, unsigned long long* chunk_counter)
 {
     extern __shared__ double sm_tables[];
+    __shared__ int64_t flag_queue[(kBlock / 32) * kFlagQueue];
     const GridView g = stage_tables(kg, sm_tables);
     double* qt = sm_tables + table_doubles_smem + threadIdx.x;
     int* qr = reinterpret_cast<int*>(sm_tables + table_doubles_smem + 3 * kQueue * kBlock) + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < n_words; w0 += warps * 32) {
-        // 32 mask words per warp and step; most are empty
-        const uint32_t mine = w0 + lane < n_words ? __ldg(mask + w0 + lane) : 0u;
-        uint32_t nonzero = __ballot_sync(0xffffffffu, mine != 0u);
-        for (; nonzero; nonzero &= nonzero - 1) {
-            const int src = __ffs(nonzero) - 1;
-            const uint32_t m = __shfl_sync(0xffffffffu, mine, src);
-            const int64_t i = ((w0 + src) << 5) + lane;
-            const bool active = (m >> lane) & 1u;
-            double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
-            RayConsts c;
-            if (active) { load_ray(kr, i, x, d); ray_setup(c, x, d); }
-            typename Op::Sink sink = op.begin(active ? i : 0);
-            walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
-            if (active) op.end(i, sink);
-            __syncwarp();
-        }
-    }
+    for_each_flagged(mask, n_words, chunk_counter, flag_queue + (threadIdx.x >> 5) * kFlagQueue,
+                     [&](int64_t i, bool active) {
+        double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
+        RayConsts c;
+        if (active) { load_ray(kr, i, x, d); ray_setup(c, x, d); }
+        typename Op::Sink sink = op.begin(active ? i : 0);
+        walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+        if (active) op.end(i, sink);
+    });
 }
 
 // Warp-cooperative walker (sphrt_coop.cuh): persistent warps, 32 rays per tile; phase 0 plans
@@ -478,9 +522,11 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
 template <class Op>
 __global__ void __launch_bounds__(kListBlock)
 walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, int64_t n_words,
-                   int table_doubles_smem, double* glist_t, int* glist_r)
+                   int table_doubles_smem, double* glist_t, int* glist_r,
+                   unsigned long long* chunk_counter)
 {
     extern __shared__ double sm_tables[];
+    __shared__ int64_t flag_queue[(kListBlock / 32) * kFlagQueue];
     const GridView g = stage_tables(kg, sm_tables);
     const int cap = 2 * (kg.ne + 1);
     ConeList list;
@@ -492,12 +538,9 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, 
         const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         list = ConeList{glist_t + tid * cap, glist_r + tid * cap, 1, cap};
     }
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
-        const uint32_t m = __ldg(listed_mask + w);
-        if (!((m >> lane) & 1u)) continue;
-        const int64_t i = (w << 5) + lane;
+    for_each_flagged(listed_mask, n_words, chunk_counter, flag_queue + (threadIdx.x >> 5) * kFlagQueue,
+                     [&](int64_t i, bool active) {
+        if (!active) return;
         double x[3], d[3];
         load_ray(kr, i, x, d);
         RayConsts c;
@@ -505,7 +548,7 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, 
         typename Op::Sink sink = op.begin(i);
         walk_ray<true>(g, c, x, list, sink);
         op.end(i, sink);
-    }
+    });
 }
 
 __global__ void find_starts_kernel(sphrt_grid kg, int64_t n, const double* xs, int32_t* out)
@@ -637,7 +680,8 @@ int cuda_status()
 
 template <class Op>
 int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const uint32_t* mask,
-                  void* lists, size_t smem, const ListPlan& lp, cudaStream_t st)
+                  void* lists, size_t smem, const ListPlan& lp, unsigned long long* chunk_counter,
+                  cudaStream_t st)
 {
     double* glist_t = nullptr;
     int* glist_r = nullptr;
@@ -648,7 +692,8 @@ int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const u
     if (lp.smem > 48 * 1024)
         cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
     walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
-        *grid, kr, op, mask, (kr.n + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r);
+        *grid, kr, op, mask, (kr.n + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r,
+        chunk_counter);
     return cuda_status();
 }
 
@@ -669,13 +714,15 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     uint32_t* mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
     void* lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
     const int64_t n_words = (rays->n_rays + 31) / 32;
+    // work hand-out counters: [0] cooperative tiles, [1] masked per-thread pass, [2] listed pass
+    unsigned long long* counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
+    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st);
 
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid))) {
             cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            unsigned long long* tile_counter = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
-            cudaMemsetAsync(tile_counter, 0, sizeof(unsigned long long), st);
+            unsigned long long* tile_counter = counters;
             walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
                 *grid, kr, op, cl.P, mask, mask_tracked, tile_counter, stats);
             int rc = cuda_status();
@@ -690,10 +737,10 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
             if (blocks_m > want) blocks_m = want;
             if (blocks_m < 1) blocks_m = 1;
             walk_tracked_masked_kernel<Op><<<(unsigned)blocks_m, kBlock, smem_a, st>>>(
-                *grid, kr, op, (int)(smem / sizeof(double)), mask_tracked, n_words);
+                *grid, kr, op, (int)(smem / sizeof(double)), mask_tracked, n_words, counters + 1);
             rc = cuda_status();
             if (rc != SPHRT_OK) return rc;
-            return launch_listed(grid, kr, op, mask, lists, smem, lp, st);
+            return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
             }
         }
     }
@@ -707,7 +754,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
                                                                        (int)(smem / sizeof(double)), mask);
     int rc = cuda_status();
     if (rc != SPHRT_OK) return rc;
-    return launch_listed(grid, kr, op, mask, lists, smem, lp, st);
+    return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
     }
 }
 
