@@ -1,0 +1,27 @@
+#!/usr/bin/env python3
+"""Key metrics of an `ncu --set full` report as a small CSV (what profiles/ keeps).
+usage: ncu -i X.ncu-rep --page raw --csv > raw.csv ; ncu_summary.py raw.csv out.csv"""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+KEYS = ['gpu__time_duration.sum', 'launch__block_size', 'launch__grid_size', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum',
+        'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
+ki = hdr.index('Kernel Name')
+with open(sys.argv[2], 'w', newline='') as f:
+    w = csv.writer(f)
+    w.writerow(['metric', 'unit'] + [r[ki].replace('<unnamed>::', '')[:70] for r in rows[2:]])
+    for k in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            w.writerow([k, units[i]] + [r[i] for r in rows[2:]])
+print(open(sys.argv[2]).read())
