@@ -89,18 +89,25 @@ SPHRT_COLD void coop_locate_point(const GridView& g, double p0, double p1, doubl
 }
 
 // ---- phase 0: classify one ray and plan its candidate ranges ---------------------------------
-__device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
-                                             const CoopPlan& P, CoopRecord& rec)
+// elevation bin of a point from its cosine: last cone with cos e_i >= cos e (the table descends)
+__device__ __forceinline__ int coop_bin_cos(const GridView& g, double cosv)
 {
-    if (ray_needs_cone_list(c, g.c2_sorted(), g.n_c2)) return COOP_LISTED;
-    if (!g.wrap) return COOP_TRACKED;             // partial azimuth range: gap sector logic
-    int bins[3], st[3];
-    double sph[3];
-    coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
-    const bool on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
-                             near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
-    if (bins[0] != g.nr || on_boundary) return COOP_TRACKED;      // starts inside / on a boundary
-    if (ray_has_snapped_aa(c, g.c2_sorted(), g.n_c2)) return COOP_TRACKED;   // see sphrt_walker.cuh
+    const double* ce = g.cos_e();
+    int lo = 0, hi = g.ne + 1;                     // first index with ce[idx] < cosv
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ce[mid] >= cosv) lo = mid + 1; else hi = mid; }
+    return lo - 1;
+}
+
+// Start points are shared by whole observations: their classification is cached per lane.
+struct CoopStartCache {
+    int64_t index; bool generic;                   // generic: inside the grid or on a cone / half-plane
+};
+
+__device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
+                                             const CoopPlan& P, int64_t start_index,
+                                             CoopStartCache& cache, CoopRecord& rec)
+{
+    // a ray that never reaches the outermost shell has no segment, whatever else holds for it
     if (c.dperp2 != c.dperp2) return COOP_MISS;                   // no radial root at all
     const double rN = g.r_b()[g.nr];
     const double argN = rN * rN - c.dperp2;
@@ -108,6 +115,18 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     const double sN = sqrt(argN);
     const double t_in = c.tc - sN, t_out = c.tc + sN;
     if (t_out < 0) return COOP_MISS;                              // the grid lies behind the start
+    if (ray_needs_cone_list(c, g.c2_sorted(), g.n_c2)) return COOP_LISTED;
+    if (!g.wrap) return COOP_TRACKED;             // partial azimuth range: gap sector logic
+    if (start_index != cache.index) {
+        int bins[3], st[3];
+        double sph[3];
+        coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
+        cache.index = start_index;
+        cache.generic = bins[0] != g.nr || near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
+                        near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+    }
+    if (cache.generic) return COOP_TRACKED;                       // starts inside / on a boundary
+    if (ray_has_snapped_aa(c, g.c2_sorted(), g.n_c2)) return COOP_TRACKED;   // see sphrt_walker.cuh
     if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return COOP_TRACKED;
     // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
     int lo = 0, hi = g.nr;
@@ -120,16 +139,20 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     rec.d0 = c.d0; rec.d1 = c.d1; rec.d2 = c.d2;
     rec.tc = c.tc; rec.dperp2 = c.dperp2;
 
-    // entry / exit points and the voxel state at entry (as walk_ray_fast's fast-forward)
+    // voxel state at the entry point (as walk_ray_fast's fast-forward): exact, float64
     const double p[3] = {c.d0 * t_in + c.x0, c.d1 * t_in + c.x1, c.d2 * t_in + c.x2};
     const double q[3] = {c.d0 * t_out + c.x0, c.d1 * t_out + c.x1, c.d2 * t_out + c.x2};
-    int pb[3], ps[3], qb[3], qs[3];
-    double psph[3], qsph[3];
+    int pb[3], ps[3];
+    double psph[3];
     coop_locate_point(g, p[0], p[1], p[2], pb, ps, psph);
     rec.se0 = ps[1]; rec.sa0 = ps[2];
-    coop_locate_point(g, q[0], q[1], q[2], qb, qs, qsph);
-    const double qe = qsph[1];
-    const int qb_e = qb[1], qb_a = qb[2];
+    // the bins of the exit and turning points only size the candidate ranges, whose two ends are
+    // guards: cosines and a float atan2 are accurate enough (an off-by-one trips a guard)
+    const double cos_p = p[2] / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    const double cos_q = q[2] / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    const int qb_e = coop_bin_cos(g, cos_q);
+    int qs_a;
+    const int qb_a = locate(g.a_b(), g.na, (double)atan2f((float)q[1], (float)q[0]), &qs_a);
 
     // ---- elevation: colatitude is unimodal along the chord; turning point at t*
     const double den = c.d2 * c.dx - c.x2;
@@ -138,21 +161,18 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     double t_turn = -SPHRT_INF;
     if (tstar > t_in && tstar < t_out) {
         const double m[3] = {c.d0 * tstar + c.x0, c.d1 * tstar + c.x1, c.d2 * tstar + c.x2};
-        int mbins[3], mst[3];
-        double msph[3];
-        coop_locate_point(g, m[0], m[1], m[2], mbins, mst, msph);
-        const double me = msph[1];
-        const int mb = mbins[1];
+        const double cos_m = m[2] / sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        const int mb = coop_bin_cos(g, cos_m);
         t_turn = tstar;
         const int top = pb[1] > qb_e ? pb[1] : qb_e, bot = pb[1] < qb_e ? pb[1] : qb_e;
-        if (me < psph[1]) { step = +1; first = mb; count = top + 2 - mb; }        // dips towards +Z
-        else              { step = -1; first = mb + 1; count = mb + 2 - bot; }    // rises towards -Z
+        if (cos_m > cos_p) { step = +1; first = mb; count = top + 2 - mb; }       // dips towards +Z
+        else               { step = -1; first = mb + 1; count = mb + 2 - bot; }   // rises towards -Z
         // first crossings (entry -> turn) fill the buffer downwards from `mid`, second crossings
         // (turn -> exit) upwards; a chord's colatitude varies by less than pi in total
         mid = (pb[1] > mb ? pb[1] - mb : mb - pb[1]) + 2;
         up = (qb_e > mb ? qb_e - mb : mb - qb_e) + 2;
-    } else if (qe >= psph[1]) { step = +1; first = pb[1]; count = qb_e + 2 - pb[1]; up = count; }
-    else                      { step = -1; first = pb[1] + 1; count = pb[1] + 2 - qb_e; up = count; }
+    } else if (cos_q <= cos_p) { step = +1; first = pb[1]; count = qb_e + 2 - pb[1]; up = count; }
+    else                       { step = -1; first = pb[1] + 1; count = pb[1] + 2 - qb_e; up = count; }
     if (count < 2 || mid + up + 1 > P.capE) return COOP_TRACKED;
     rec.e_first = first; rec.e_count = count; rec.e_step = step; rec.t_turn = t_turn; rec.e_mid = mid;
 

@@ -426,7 +426,10 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 
 // Warp-cooperative walker (sphrt_coop.cuh): persistent warps, 32 rays per tile; phase 0 plans
 // one ray per lane, phase 1 walks the tile's rays one after the other with all 32 lanes.
-constexpr int kCoopMaxWarps = 16;
+#ifndef SPHRT_COOP_WARPS
+#define SPHRT_COOP_WARPS 16
+#endif
+constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
 constexpr int kCoopRecDoubles = 6;
 
 template <class Op>
@@ -441,6 +444,11 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
     double* recd = reinterpret_cast<double*>(wbase + P.off_rec);
     const int64_t n_tiles = (kr.n + 31) >> 5;
     unsigned long long n_coop = 0, n_handed = 0;
+    CoopStartCache start_cache{-1, true};
+    // the cooperative ranges assume cos(e_b) descends (e_b ascending within [0, pi])
+    bool table_ok = true;
+    for (int k = threadIdx.x; k < g.ne; k += blockDim.x) table_ok &= g.cos_e()[k] > g.cos_e()[k + 1];
+    table_ok = __syncthreads_and(table_ok);
     for (;;) {
         // tiles are handed out dynamically: their cost varies from nothing (misses) to ~1 ms
         unsigned long long next = 0;
@@ -451,13 +459,16 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
         const int64_t i = (tile << 5) + lane;
         int cls = COOP_MISS;
         int ri0 = 0, ri1 = 0, ri2 = 0, ri3 = 0, ri4 = 0, ri5 = 0;      // integer part of the record
+        int64_t start_index = 0;
         if (i < kr.n) {
             double x[3], d[3];
             load_ray(kr, i, x, d);
+            start_index = i / kr.rps;
             RayConsts c;
             ray_setup(c, x, d);
             CoopRecord rec;
-            cls = coop_plan_ray(g, c, x, P, rec);
+            cls = coop_plan_ray(g, c, x, P, start_index, start_cache, rec);
+            if (!table_ok && cls == COOP_RAY) cls = COOP_TRACKED;
             if (cls == COOP_RAY) {
                 recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
                 recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
@@ -493,7 +504,7 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
             rec.a_first = __shfl_sync(0xffffffffu, ri3, j);
             rec.a_dir = ac < 0 ? -1 : 1; rec.a_count = ac < 0 ? -ac : ac;
             rec.se0 = (int)(int16_t)(stt & 0xffff); rec.sa0 = stt >> 16;
-            const double* xs = kr.starts + 3 * (ray / kr.rps);
+            const double* xs = kr.starts + 3 * __shfl_sync(0xffffffffu, start_index, j);
             const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
             CoopLists L;
             if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_tracked |= 1u << j; n_handed++; continue; }
