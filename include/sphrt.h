@@ -109,6 +109,25 @@ int sphrt_trace_segments(const sphrt_grid *grid, const sphrt_rays *rays, int64_t
                          int32_t *vox, double *seg_len, int32_t *count,
                          void *scratch, int64_t scratch_bytes, void *stream);
 
+/* Stored operator (optional).  The reference precomputes and stores its operator
+ * (Operator.regs / .lens, raytracer.py:675-679: 32 bytes for each of K padded slots per ray) and
+ * applies it with a gather (:710-713).  For problems that apply one operator many times and have
+ * the memory, the canonical segments can be stored here too, 8 bytes per segment (12 with
+ * float64 lengths): offsets (n_rays + 1) int64 = exclusive prefix sum of sphrt_count_segments,
+ * vox[offsets[i] + k] = flat voxel offset (r*ne + e)*na + a of segment k of ray i, seg_len its
+ * length (len_dtype SPHRT_F32 / SPHRT_F64).  sphrt_forward_stored / sphrt_adjoint_stored then
+ * apply it exactly like sphrt_forward / sphrt_adjoint (same n_vol / rays_per_vol rules) without
+ * tracing; they stream the lists once (HBM-bound). */
+int sphrt_store_segments(const sphrt_grid *grid, const sphrt_rays *rays, const int64_t *offsets,
+                         int32_t *vox, void *seg_len, int len_dtype,
+                         void *scratch, int64_t scratch_bytes, void *stream);
+int sphrt_forward_stored(const int64_t *offsets, const int32_t *vox, const void *seg_len, int len_dtype,
+                         int64_t n_rays, const void *density, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void *out, void *stream);
+int sphrt_adjoint_stored(const int64_t *offsets, const int32_t *vox, const void *seg_len, int len_dtype,
+                         int64_t n_rays, const void *y, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void *grad, void *stream);
+
 /* Parity export of the warp-cooperative walker (the kernel that serves large grids): for
  * every ray it handles itself, ALL its events in merged order -- the reference's sorted
  * candidate list (raytracer.py:131-170) restricted to the chord inside the outermost shell:

@@ -280,6 +280,37 @@ struct TraceOp {
     __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
 };
 
+// Stored operator: the canonical segments of every ray written once as a
+// compact CSR list -- flat voxel offset (int32) + length (float32 or float64) per segment,
+// 8 or 12 bytes against the reference's 32 bytes for each of its K padded slots per ray
+// (raytracer.py:66-72, 675-679) -- for problems that apply the same operator many times.
+template <typename L>
+struct StoreOp {
+    const int64_t* offsets; int32_t* vox; L* seg_len; int ne, na;
+    struct Sink {
+        int32_t* vox; L* len; int ne, na;
+        int cur; double acc; int64_t n;          // pending segment (consecutive identical voxels merge)
+        __device__ __forceinline__ void segment(int r, int e, int a, double l)
+        {
+            const int idx = (r * ne + e) * na + a;
+            if (idx == cur) { acc += l; return; }
+            if (cur >= 0) { vox[n] = cur; len[n] = (L)acc; n++; }
+            cur = idx; acc = l;
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        const int64_t o = __ldg(offsets + ray);
+        return Sink{vox + o, seg_len + o, ne, na, -1, 0.0, 0};
+    }
+    __device__ __forceinline__ void end(int64_t, Sink& s) const
+    {
+        if (s.cur >= 0) { s.vox[s.n] = s.cur; s.len[s.n] = (L)s.acc; }
+    }
+    static constexpr bool kCoop = false, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
+};
+
 // Raw event export of the warp-cooperative walker (parity tests): every event of a ray at its
 // rank in the merged order, with the voxel that follows it and the length up to the next
 // event (0 where the reference zeroes the slot).  count stays untouched for rays that the
@@ -791,6 +822,77 @@ int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in
     return SPHRT_OK;
 }
 
+// ---- stored operator: apply passes ---------------------------------------------------------------
+// One warp per ray streams the ray's (voxel, length) pairs with coalesced loads; the volume is
+// gathered from L2.  Bound by HBM: 8 B (12 B for float64 lengths) per segment.
+constexpr int kStoredBlock = 256;
+
+template <typename T, typename L, bool kAdjoint>
+__global__ void __launch_bounds__(kStoredBlock)
+stored_apply_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ vox,
+                    const L* __restrict__ seg_len, int64_t n_rays, const T* __restrict__ in,
+                    T* __restrict__ out, int64_t n_vol, int64_t rays_per_vol, int64_t nvox)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < n_rays; ray += warps) {
+        const int64_t b = __ldg(offsets + ray), e = __ldg(offsets + ray + 1);
+        if (b == e && kAdjoint) continue;
+        const int64_t v0 = rays_per_vol > 0 ? (ray / rays_per_vol) % n_vol : 0;
+        const int64_t nv = rays_per_vol > 0 ? 1 : n_vol;          // channels share the list
+        for (int64_t v = 0; v < nv; v++) {
+            if constexpr (kAdjoint) {
+                // in = y (n_vol, n_rays) or (n_rays); out = gradient volumes
+                const double w = (double)__ldg(in + (rays_per_vol > 0 ? ray : v * n_rays + ray));
+                if (w == 0.0) continue;
+                T* vol = out + (v0 + v) * nvox;
+                for (int64_t k = b + lane; k < e; k += 32)
+                    atomicAdd(vol + __ldcs(vox + k), (T)(w * (double)__ldcs(seg_len + k)));
+            } else {
+                const T* vol = in + (v0 + v) * nvox;
+                double acc = 0.0;
+                for (int64_t k = b + lane; k < e; k += 32)
+                    acc = fma_rn((double)__ldg(vol + __ldcs(vox + k)), (double)__ldcs(seg_len + k), acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) out[rays_per_vol > 0 ? ray : v * n_rays + ray] = (T)acc;
+            }
+        }
+    }
+}
+
+template <typename T, typename L, bool kAdjoint>
+int launch_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int64_t n_rays,
+                  const void* in, void* out, int64_t n_vol, int64_t rays_per_vol, int64_t nvox,
+                  void* stream)
+{
+    if (n_rays == 0) return SPHRT_OK;
+    int64_t blocks = (int64_t)num_sms() * (2048 / kStoredBlock);
+    const int64_t want = (n_rays * 32 + kStoredBlock - 1) / kStoredBlock;
+    if (blocks > want) blocks = want;
+    stored_apply_kernel<T, L, kAdjoint><<<(unsigned)blocks, kStoredBlock, 0, (cudaStream_t)stream>>>(
+        offsets, vox, (const L*)seg_len, n_rays, (const T*)in, (T*)out, n_vol, rays_per_vol, nvox);
+    return cuda_status();
+}
+
+template <bool kAdjoint>
+int dispatch_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
+                    int64_t n_rays, const void* in, int dtype, void* out, int64_t n_vol,
+                    int64_t rays_per_vol, int64_t nvox, void* stream)
+{
+    if (n_rays < 0 || n_vol < 1 || rays_per_vol < 0 || nvox < 1) return SPHRT_EINVAL;
+    if (n_rays > 0 && (!offsets || !in || !out)) return SPHRT_EINVAL;
+    if (dtype == SPHRT_F32 && len_dtype == SPHRT_F32)
+        return launch_stored<float, float, kAdjoint>(offsets, vox, seg_len, n_rays, in, out, n_vol, rays_per_vol, nvox, stream);
+    if (dtype == SPHRT_F32 && len_dtype == SPHRT_F64)
+        return launch_stored<float, double, kAdjoint>(offsets, vox, seg_len, n_rays, in, out, n_vol, rays_per_vol, nvox, stream);
+    if (dtype == SPHRT_F64 && len_dtype == SPHRT_F64)
+        return launch_stored<double, double, kAdjoint>(offsets, vox, seg_len, n_rays, in, out, n_vol, rays_per_vol, nvox, stream);
+    if (dtype == SPHRT_F64 && len_dtype == SPHRT_F32)
+        return launch_stored<double, float, kAdjoint>(offsets, vox, seg_len, n_rays, in, out, n_vol, rays_per_vol, nvox, stream);
+    return SPHRT_EINVAL;
+}
+
 }  // namespace
 
 // ---- C ABI --------------------------------------------------------------------------------------
@@ -877,6 +979,40 @@ int sphrt_trace_segments(const sphrt_grid* grid, const sphrt_rays* rays, int64_t
     if (rays->n_rays > 0 && (!vox || !seg_len || !count)) return SPHRT_EINVAL;
     const TraceOp op{vox, seg_len, count, max_seg};
     return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_store_segments(const sphrt_grid* grid, const sphrt_rays* rays, const int64_t* offsets,
+                         int32_t* vox, void* seg_len, int len_dtype, void* scratch,
+                         int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays > 0 && (!offsets || !vox || !seg_len)) return SPHRT_EINVAL;
+    if (len_dtype == SPHRT_F32) {
+        const StoreOp<float> op{offsets, vox, (float*)seg_len, grid->ne, grid->na};
+        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+    }
+    if (len_dtype == SPHRT_F64) {
+        const StoreOp<double> op{offsets, vox, (double*)seg_len, grid->ne, grid->na};
+        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+    }
+    return SPHRT_EINVAL;
+}
+
+int sphrt_forward_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
+                         int64_t n_rays, const void* density, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void* out, void* stream)
+{
+    return dispatch_stored<false>(offsets, vox, seg_len, len_dtype, n_rays, density, dtype, out, n_vol,
+                                  rays_per_vol, nvox, stream);
+}
+
+int sphrt_adjoint_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
+                         int64_t n_rays, const void* y, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void* grad, void* stream)
+{
+    return dispatch_stored<true>(offsets, vox, seg_len, len_dtype, n_rays, y, dtype, grad, n_vol,
+                                 rays_per_vol, nvox, stream);
 }
 
 int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_ev,
