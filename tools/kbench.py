@@ -18,7 +18,7 @@ def run(spec, reps=7):
     name, _, obs = spec.partition(":")
     grid, geoms, _ = bench.workload(name, int(obs) if obs else None)
     geom = S.ViewGeomCollection(*geoms) if len(geoms) > 1 or grid.dynamic else geoms[0]
-    op = S.Operator(grid, geom)
+    op = S.Operator(grid, geom, store_segments=bool(os.environ.get('SPHRT_STORE')))
     shape = tuple(grid.shape)
     x = torch.rand(shape, device="cuda")
     y = torch.rand(op._rays.shape, device="cuda")
@@ -31,7 +31,8 @@ def run(spec, reps=7):
         if k >= 2:
             tf.append(a.elapsed_time(b)); ta.append(b.elapsed_time(c))
     _, nseg = op.segment_counts()
-    print(f"{os.environ.get('SPHRT_LIB', 'default'):40s} {spec:8s} fwd {np.median(tf):8.3f} ms (min {min(tf):.3f})  "
+    mode = os.environ.get('SPHRT_LIB', 'default') + (' stored %.2f GB' % (op.stored_bytes / 1e9) if op.stored_bytes else '')
+    print(f"{mode:40s} {spec:8s} fwd {np.median(tf):8.3f} ms (min {min(tf):.3f})  "
           f"adj {np.median(ta):8.3f} ms (min {min(ta):.3f})  seg/s fwd+adj {2 * nseg / (np.median(tf) + np.median(ta)) * 1e3:.3e}")
 
 
