@@ -281,12 +281,22 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
             const ConeQuad q = cone_quadratic(g, c, i);
             double t1, t2;
             cone_roots(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
-            if (t1 >= t_in && t1 <= t_out) { const Event e = cone_event(g, c, i, t1); ta = e.t; ra = e.region; }
-            if (t2 >= t_in && t2 <= t_out) { const Event e = cone_event(g, c, i, t2); tb = e.t; rb = e.region; }
-            if (tb < ta) { const double tt = ta; ta = tb; tb = tt; const int rr = ra; ra = rb; rb = rr; }
+            // keep the roots inside the chord that lie on the cone's own nappe (cone_event);
+            // the region is only worked out for those
+            const bool v1 = t1 >= t_in && t1 <= t_out && !cone_shadow(g, c, i, t1);
+            const bool v2 = t2 >= t_in && t2 <= t_out && !cone_shadow(g, c, i, t2);
+            if (v1) ta = t1;
+            if (v2) { if (v1) tb = t2; else ta = t2; }
+            if (tb < ta) { const double tt = ta; ta = tb; tb = tt; }
             if (tb == ta) tb = SPHRT_INF;                      // merged double root: one event
+            int geo;
+            if (ta < SPHRT_INF) ra = cone_region(g, c, i, ta, &geo);
             // the candidates at both ends of the range are guards: they must stay silent
             if ((k == 0 || k == rec.e_count - 1) && ta < SPHRT_INF) bad = true;
+        }
+        if (__any_sync(SPHRT_FULL, tb < SPHRT_INF)) {           // cones crossed twice inside the chord
+            int geo;
+            if (tb < SPHRT_INF) rb = cone_region(g, c, i, tb, &geo);
         }
         const bool a_down = ta < rec.t_turn;                    // first crossing (towards the turn)
         const bool a_up = ta < SPHRT_INF && !a_down;
@@ -325,8 +335,23 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
             int pl = rec.a_first + k * rec.a_dir;              // seam: plane na going up, 0 going down
             if (pl > g.na) pl -= g.na;
             if (pl < 0) pl += g.na;
-            FastAzimuth::eval(g, c, pl, t_in, false, t, geo);
-            if (!(t <= t_out)) t = SPHRT_INF;
+            if (pl == 0 || pl == g.na) {
+                // the seam: one half-plane the reference evaluates twice, earlier root wins
+                FastAzimuth::eval(g, c, pl, t_in, false, t, geo);
+                if (!(t <= t_out)) t = SPHRT_INF;
+            } else {
+                // plane_event() with the validity kept in a predicate
+                const double ca = g.cos_a()[pl], sa = g.sin_a()[pl];
+                const double num = fma_rn(0.0, c.x2, fma_rn(ca, c.x1, (-sa) * c.x0));
+                const double den = fma_rn(0.0, c.d2, fma_rn(ca, c.d1, (-sa) * c.d0));
+                const double tt = -num / den;
+                const double cross = fma_rn(ca, c.d1, -(sa * c.d0));
+                geo = pl - (cross < 0 ? 1 : 0);
+                const double px = tt * c.d0 + c.x0, py = tt * c.d1 + c.x1;
+                const bool valid = !(fabs(cross) <= SPHRT_A_PARALLEL) && !(ca * px + sa * py < 0) &&
+                                   tt >= t_in && tt <= t_out;
+                if (valid) t = tt;
+            }
             if (k == rec.a_count - 1 && t < SPHRT_INF) bad = true;     // guard
         }
         const uint32_t mv = __ballot_sync(SPHRT_FULL, t < SPHRT_INF);

@@ -179,22 +179,36 @@ SPHRT_HD void cone_roots(const ConeQuad& q, double delta, double& t1, double& t2
     if (q.aa == 0 && q.bb == 0 && q.cc == 0) { t1 = SPHRT_INF; t2 = SPHRT_INF; }
 }
 
-// region / shadow / NaN handling of one cone root (:418-466)
-SPHRT_HD Event cone_event(const GridView& g, const RayConsts& c, int i, double t)
+// region a ray enters through cone i at distance t (:418-446, 464): sign of d . (p x phi_hat),
+// glancing crossings leave the index unchanged (-2)
+SPHRT_HD int cone_region(const GridView& g, const RayConsts& c, int i, double t, int* geo)
 {
-    Event ev;
     const double p0 = c.d0 * t + c.x0, p1 = c.d1 * t + c.x1, p2 = c.d2 * t + c.x2;
     const double n0 = -(p2 * p0), n1 = -(p2 * p1), n2 = fma_rn(p0, p0, p1 * p1);
     const double prod = dot3(c.d0, c.d1, c.d2, n0, n1, n2);
     const int neg = prod > 0;
-    ev.geo = i - neg;
-    int region = ev.geo;
+    *geo = i - neg;
+    int region = i - neg;
     if (fabs(prod) < SPHRT_TAU) region = -2;
+    if (region == g.ne) region = -1;
+    return region;
+}
+
+// true if the root at distance t lies on the mirror nappe of cone i (:449-461)
+SPHRT_HD bool cone_shadow(const GridView& g, const RayConsts& c, int i, double t)
+{
+    const double p2 = c.d2 * t + c.x2;
     bool shadow = (p2 >= 0) != (g.cos_e()[i] >= 0);
     if (fabs(SPHRT_HALF_PI - g.e_b()[i]) < SPHRT_TAU) shadow = false;
-    if (shadow) t = SPHRT_INF;
-    if (region == g.ne) region = -1;
-    ev.region = region;
+    return shadow;
+}
+
+// region / shadow / NaN handling of one cone root (:418-466)
+SPHRT_HD Event cone_event(const GridView& g, const RayConsts& c, int i, double t)
+{
+    Event ev;
+    ev.region = cone_region(g, c, i, t, &ev.geo);
+    if (cone_shadow(g, c, i, t)) t = SPHRT_INF;
     ev.t = (t != t) ? SPHRT_INF : t;
     return ev;
 }
