@@ -731,7 +731,7 @@ int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const u
         glist_t = (double*)lists;
         glist_r = (int*)(glist_t + lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1));
     }
-    if (lp.smem > 48 * 1024)
+    if (lp.smem > 40 * 1024)       // (+ the static flag queue)
         cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
     walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
         *grid, kr, op, mask, (kr.n + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r,
@@ -771,7 +771,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
             if (rc != SPHRT_OK) return rc;
             if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
             else {
-            if (smem_a > 48 * 1024)
+            if (smem_a > 40 * 1024)   // (+ the static flag queue)
                 cudaFuncSetAttribute(walk_tracked_masked_kernel<Op>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
             int64_t blocks_m = (int64_t)num_sms() * SPHRT_TRACKED_MIN_BLOCKS;

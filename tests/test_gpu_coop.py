@@ -258,3 +258,18 @@ def test_coop_multichannel_and_dynamic(S, walker):
     walker("tracked"); yt = opd(vol); gt = opd.T(w)
     assert torch.allclose(yc, yt, rtol=1e-12, atol=1e-13)
     assert torch.allclose(gc, gt, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("n", [150, 200, 230])
+def test_grid_sizes_around_the_48k_shared_memory_boundary(S, walker, n):
+    """Boundary tables of 8-13 KB put static + dynamic shared memory of the fallback kernels next
+    to the 48 KB opt-in limit (a (200,200,200) grid failed to launch once)."""
+    grid = S.SphericalGrid((n, n, n), size_r=(0.5, 5))
+    g = S.ConeRectGeom((64, 64), (80.0, 10.0, 20.0), fov=(7, 7))
+    op = S.Operator(grid, g)
+    x = torch.rand(tuple(grid.shape), device="cuda", dtype=torch.float64)
+    walker("tracked"); a = op._apply_forward(x)
+    walker("coop"); b = op._apply_forward(x)
+    assert torch.allclose(a, b, rtol=1e-12, atol=1e-12)
+    cnt, total = op.segment_counts()
+    assert total > 0
