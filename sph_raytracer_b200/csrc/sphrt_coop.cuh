@@ -101,6 +101,7 @@ __device__ __forceinline__ int coop_bin_cos(const GridView& g, double cosv)
 // Start points are shared by whole observations: their classification is cached per lane.
 struct CoopStartCache {
     int64_t index; bool generic;                   // generic: inside the grid or on a cone / half-plane
+    int se, sa, a_bin;                             // reference states and azimuth bin of the start
 };
 
 __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
@@ -115,8 +116,12 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     const double sN = sqrt(argN);
     const double t_in = c.tc - sN, t_out = c.tc + sN;
     if (t_out < 0) return COOP_MISS;                              // the grid lies behind the start
-    if (ray_needs_cone_list(c, g.c2_sorted(), g.n_c2)) return COOP_LISTED;
-    if (!g.wrap) return COOP_TRACKED;             // partial azimuth range: gap sector logic
+    // Rays whose cone roots lose adjacency (snapped discriminant or leading coefficient,
+    // ray_needs_cone_list) are walked from t = 0 with EVERY cone evaluated and the roots sorted
+    // explicitly ("all-cones mode", e_mid == 0)
+    const bool listed = ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);
+    const int hand_over = listed ? COOP_LISTED : COOP_TRACKED;
+    if (!g.wrap) return hand_over;                // partial azimuth range: gap sector logic
     if (start_index != cache.index) {
         int bins[3], st[3];
         double sph[3];
@@ -124,10 +129,11 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
         cache.index = start_index;
         cache.generic = bins[0] != g.nr || near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
                         near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+        cache.se = st[1]; cache.sa = st[2]; cache.a_bin = bins[2];
     }
-    if (cache.generic) return COOP_TRACKED;                       // starts inside / on a boundary
-    if (ray_has_snapped_aa(c, g.c2_sorted(), g.n_c2)) return COOP_TRACKED;   // see sphrt_walker.cuh
-    if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return COOP_TRACKED;
+    if (cache.generic) return hand_over;                          // starts inside / on a boundary
+    if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return hand_over;
+    const bool all_cones = listed;
     // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
     int lo = 0, hi = g.nr;
     while (lo < hi) {
@@ -139,20 +145,26 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     rec.d0 = c.d0; rec.d1 = c.d1; rec.d2 = c.d2;
     rec.tc = c.tc; rec.dperp2 = c.dperp2;
 
+    const double q[3] = {c.d0 * t_out + c.x0, c.d1 * t_out + c.x1, c.d2 * t_out + c.x2};
+    int qs_a;
+    const int qb_a = locate(g.a_b(), g.na, (double)atan2f((float)q[1], (float)q[0]), &qs_a);
+    int a_bin_in;
+    if (all_cones) {
+        // walk from the start point: its states, all cones, planes from its sector
+        rec.se0 = cache.se; rec.sa0 = cache.sa; a_bin_in = cache.a_bin;
+        rec.e_first = 0; rec.e_count = g.ne + 1; rec.e_step = 1; rec.t_turn = -SPHRT_INF; rec.e_mid = 0;
+    } else {
     // voxel state at the entry point (as walk_ray_fast's fast-forward): exact, float64
     const double p[3] = {c.d0 * t_in + c.x0, c.d1 * t_in + c.x1, c.d2 * t_in + c.x2};
-    const double q[3] = {c.d0 * t_out + c.x0, c.d1 * t_out + c.x1, c.d2 * t_out + c.x2};
     int pb[3], ps[3];
     double psph[3];
     coop_locate_point(g, p[0], p[1], p[2], pb, ps, psph);
-    rec.se0 = ps[1]; rec.sa0 = ps[2];
+    rec.se0 = ps[1]; rec.sa0 = ps[2]; a_bin_in = pb[2];
     // the bins of the exit and turning points only size the candidate ranges, whose two ends are
     // guards: cosines and a float atan2 are accurate enough (an off-by-one trips a guard)
     const double cos_p = p[2] / sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
     const double cos_q = q[2] / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
     const int qb_e = coop_bin_cos(g, cos_q);
-    int qs_a;
-    const int qb_a = locate(g.a_b(), g.na, (double)atan2f((float)q[1], (float)q[0]), &qs_a);
 
     // ---- elevation: colatitude is unimodal along the chord; turning point at t*
     const double den = c.d2 * c.dx - c.x2;
@@ -175,19 +187,20 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     else                       { step = -1; first = pb[1] + 1; count = pb[1] + 2 - qb_e; up = count; }
     if (count < 2 || mid + up + 1 > P.capE) return COOP_TRACKED;
     rec.e_first = first; rec.e_count = count; rec.e_step = step; rec.t_turn = t_turn; rec.e_mid = mid;
+    }
 
     // ---- azimuth: monotone rotation, direction = sign of (x x d)_z
     const double cross = c.x0 * c.d1 - c.x1 * c.d0;
-    if (!(fabs(cross) > 1e-9 * sqrt(c.nx2))) return COOP_TRACKED;     // (nearly) through the Z axis
+    if (!(fabs(cross) > 1e-9 * sqrt(c.nx2))) return hand_over;        // (nearly) through the Z axis
     const int dir = cross > 0 ? +1 : -1;
-    const int s_in = FastAzimuth::to_sector(g, pb[2]), s_out = FastAzimuth::to_sector(g, qb_a);
+    const int s_in = FastAzimuth::to_sector(g, a_bin_in), s_out = FastAzimuth::to_sector(g, qb_a);
     int sweep = (s_out - s_in) * dir;
     if (sweep < 0) sweep += g.na;
     if (sweep > g.na / 2 + 1) sweep = 0;          // rounding put the exit a sector behind the entry
     rec.a_dir = dir;
     rec.a_first = dir > 0 ? s_in + 1 : s_in;
     rec.a_count = sweep + 1;                      // the last candidate is the guard
-    if (rec.a_count > P.capA) return COOP_TRACKED;
+    if (rec.a_count > P.capA) return hand_over;
     return COOP_RAY;
 }
 
@@ -265,13 +278,54 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
 #endif
     if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
-    const double t_in = tR[0], t_out = tR[nR - 1];
+    const bool all_cones = rec.e_mid == 0;
+    // events are kept from the entry point on, or from the start point in all-cones mode
+    const double t_in = all_cones ? 0.0 : tR[0], t_out = tR[nR - 1];
 
     // ---- elevation: candidates from the turning point outwards
     double* tEbuf = reinterpret_cast<double*>(wbase + P.off_tE);
     int16_t* rEbuf = reinterpret_cast<int16_t*>(wbase + P.off_rE) + 1;
     int nDown = 0, nUp = 0;
     bool unchanged = false;
+    if (all_cones) {
+        // every cone, both roots, unsorted into the (still unused) merge buffers ...
+        double* tmpT = reinterpret_cast<double*>(wbase + P.off_tEA);
+        int32_t* tmpR = reinterpret_cast<int32_t*>(wbase + P.off_sEA) + 1;
+        int n = 0;
+        for (int k0 = 0; k0 <= g.ne; k0 += 32) {
+            const int i = k0 + lane;
+            double t1 = SPHRT_INF, t2 = SPHRT_INF;
+            bool v1 = false, v2 = false;
+            if (i <= g.ne) {
+                const ConeQuad q = cone_quadratic(g, c, i);
+                cone_roots(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
+                v1 = t1 >= t_in && t1 <= t_out && !cone_shadow(g, c, i, t1);
+                v2 = t2 >= t_in && t2 <= t_out && !cone_shadow(g, c, i, t2);
+            }
+            const uint32_t m1 = __ballot_sync(SPHRT_FULL, v1), m2 = __ballot_sync(SPHRT_FULL, v2);
+            const int s1 = n + __popc(m1 & lt_mask), s2 = n + __popc(m1) + __popc(m2 & lt_mask);
+            int geo;
+            if (v1) { if (s1 < P.capE) { tmpT[s1] = t1; tmpR[s1] = cone_region(g, c, i, t1, &geo); } else bad = true; }
+            if (v2) { if (s2 < P.capE) { tmpT[s2] = t2; tmpR[s2] = cone_region(g, c, i, t2, &geo); } else bad = true; }
+            n += __popc(m1) + __popc(m2);
+        }
+        __syncwarp();
+        // ... then to their rank (the reference's sort, :131; ties in evaluation order)
+        if (n <= P.capE) {
+            for (int e = lane; e < n; e += 32) {
+                const double te = tmpT[e];
+                int rank = 0;
+                for (int j = 0; j < n; j++) {
+                    const double tj = tmpT[j];
+                    rank += (tj < te || (tj == te && j < e)) ? 1 : 0;
+                }
+                const int reg = tmpR[e];
+                tEbuf[rank] = te; rEbuf[rank] = (int16_t)reg;
+                unchanged |= reg == -2;
+            }
+        }
+        nUp = n;
+    } else
     for (int k0 = 0; k0 < rec.e_count; k0 += 32) {
         const int k = k0 + lane;
         const int i = rec.e_first + k * rec.e_step;

@@ -332,8 +332,25 @@ SPHRT_HD bool table_hits(const double* tab, int n, double lo, double hi)
     while (a < b) { const int m = (a + b) >> 1; if (tab[m] < lo) a = m + 1; else b = m; }
     return a < n && tab[a] < hi;
 }
+// The snap |aa| < tau (:376) turns a cone's quadratic into the linear equation bb t + cc = 0 when
+// the ray's inclination matches the cone's (dz^2 ~ cos^2 e_i).  For the plane-like cone
+// e = pi/2 that root lies at HALF the distance of the real crossing (the quadratic there is the
+// perfect square (dz t + xz)^2), so for nearly horizontal rays the reference changes the
+// elevation index somewhere else than the geometry does.  The walkers reproduce that by
+// evaluating the same formulas; but a displaced root also breaks the adjacency the bin tracker
+// relies on (sequences like 71 -> 73 -> 72 in the reference), and the geometric elevation bin of
+// a point is no longer the reference's state there.  Such rays (0.1-2 % at config 5) are walked
+// from the sorted list of all cone roots, like the rays with snapped discriminants.
+SPHRT_HD bool ray_has_snapped_aa(const RayConsts& c, const double* c2_sorted, int n_c2)
+{
+    const double w = SPHRT_TAU * 1.0001;
+    if (!(c.dz2 >= w + 1e-9)) return true;         // cones within tau of pi/2 (not in the table)
+    return table_hits(c2_sorted, n_c2, c.dz2 - w, c.dz2 + w);
+}
+
 SPHRT_HD bool ray_needs_cone_list(const RayConsts& c, const double* c2_sorted, int n_c2)
 {
+    if (ray_has_snapped_aa(c, c2_sorted, n_c2)) return true;
     const double v0 = c.d2 * c.x0 - c.x2 * c.d0, v1 = c.d2 * c.x1 - c.x2 * c.d1;
     const double A = v0 * v0 + v1 * v1;
     double B = c.nx2 - c.dx * c.dx;
@@ -353,20 +370,6 @@ SPHRT_HD bool ray_needs_cone_list(const RayConsts& c, const double* c2_sorted, i
         if (table_hits(c2_sorted, n_c2, cp, c3)) return true;
     }
     return false;
-}
-
-// The snap |aa| < tau (:376) turns a cone's quadratic into the linear equation bb t + cc = 0 when
-// the ray's inclination matches the cone's (dz^2 ~ cos^2 e_i).  For the plane-like cone
-// e = pi/2 that root lies at HALF the distance of the real crossing (the quadratic there is the
-// perfect square (dz t + xz)^2), so for nearly horizontal rays the reference changes the
-// elevation index somewhere else than the geometry does.  The walkers reproduce that by
-// evaluating the same formulas, but such rays must not take shortcuts that rely on the geometric
-// elevation bin of a point (the fast-forward to the entry point).
-SPHRT_HD bool ray_has_snapped_aa(const RayConsts& c, const double* c2_sorted, int n_c2)
-{
-    const double w = SPHRT_TAU * 1.0001;
-    if (!(c.dz2 >= w + 1e-9)) return true;         // cones within tau of pi/2 (not in the table)
-    return table_hits(c2_sorted, n_c2, c.dz2 - w, c.dz2 + w);
 }
 
 // Per-thread scratch for the sorted cone-root list (element k at [k * stride]).

@@ -273,3 +273,31 @@ def test_grid_sizes_around_the_48k_shared_memory_boundary(S, walker, n):
     assert torch.allclose(a, b, rtol=1e-12, atol=1e-12)
     cnt, total = op.segment_counts()
     assert total > 0
+
+
+def test_rays_with_a_snapped_leading_coefficient(S):
+    """A ray whose inclination matches a cone's angle within the |aa| < tau snap (raytracer.py:376)
+    gets that cone's root displaced, and the reference's elevation sequence stops being adjacent
+    (71 -> 73 -> 72 ...).  Both walkers must take such rays from the sorted list of all cone roots
+    (found by tools/xcheck.py: the per-thread bin tracker used to walk them)."""
+    rays = [([41.87165449473164, -66.74590637381635, 26.85256007936145],
+             [-44.167720339167914, 68.42400838356247, -27.08770691345806]),
+            ([14.996988686600575, -80.19249035690713, -6.798118500014652],
+             [-12.336793973804266, 80.54483212839102, 6.381406568204781]),
+            ([-22.193157227915137, -58.82050434403097, -29.834515536095495],
+             [23.964697249196313, 64.51301336421729, 34.094206626620924]),
+            ([-53.171844506825096, -14.80506756622339, 45.923453476975766],
+             [62.09546843462786, 17.85875431446437, -52.85088629478713])]
+    grid = S.SphericalGrid((64, 181, 91), size_r=(0, 20))
+    geom = S.ViewGeom(torch.tensor([r[0] for r in rays], dtype=torch.float64),
+                      torch.tensor([r[1] for r in rays], dtype=torch.float64))
+    ms = 800
+    og, regs, lens, (v0, s0, c0) = _oracle_canonical(S, grid, geom, ms)
+    op = S.Operator(grid, geom)
+    cc, cv, cl, stats = _events_canonical(op, ms)
+    handled, bad = _compare_handled(cc, cv, cl, v0, s0, c0)
+    assert handled.all() and len(bad) == 0, (stats, bad)
+    vox, sl, cnt = op.segments(ms)
+    _, bad_t = _compare_handled(cnt.reshape(-1).cpu().numpy(), vox.reshape(-1, ms, 3).cpu().numpy(),
+                                sl.reshape(-1, ms).cpu().numpy(), v0, s0, c0)
+    assert len(bad_t) == 0, bad_t
