@@ -465,9 +465,13 @@ constexpr int kCoopRecDoubles = 6;
 
 template <class Op>
 __global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
-walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_mask,
-                 uint32_t* tracked_mask, unsigned long long* tile_counter, unsigned long long* stats)
+walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_mask,
+                 uint32_t* listed_mask, uint32_t* tracked_mask, unsigned long long* tile_counter,
+                 unsigned long long* stats)
 {
+    // in_mask == nullptr: every ray.  Otherwise only the flagged rays (the sorted-cone-list rays
+    // of the per-thread walker, small grids): they are walked in all-cones mode and what is left
+    // over goes to listed_mask again.
     extern __shared__ double sm_tables[];
     const GridView g = stage_tables(kg, sm_tables);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -491,7 +495,9 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
         int cls = COOP_MISS;
         int ri0 = 0, ri1 = 0, ri2 = 0, ri3 = 0, ri4 = 0, ri5 = 0;      // integer part of the record
         int64_t start_index = 0;
-        if (i < kr.n) {
+        const uint32_t sel = in_mask != nullptr ? __ldg(in_mask + tile) : 0xffffffffu;
+        if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
+        if (i < kr.n && ((sel >> lane) & 1u)) {
             double x[3], d[3];
             load_ray(kr, i, x, d);
             start_index = i / kr.rps;
@@ -510,12 +516,12 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
                 ri5 = (rec.se0 & 0xffff) | (rec.sa0 << 16);
             }
         }
-        if (cls == COOP_MISS && i < kr.n) {           // never enters the grid: empty result
+        if (cls == COOP_MISS && i < kr.n && ((sel >> lane) & 1u)) {   // never enters the grid: empty result
             typename Op::Sink none = op.begin(i);
             op.end(i, none);
         }
         const uint32_t m_ray = __ballot_sync(0xffffffffu, cls == COOP_RAY);
-        const uint32_t m_listed = __ballot_sync(0xffffffffu, cls == COOP_LISTED);
+        uint32_t m_listed = __ballot_sync(0xffffffffu, cls == COOP_LISTED);
         uint32_t m_tracked = __ballot_sync(0xffffffffu, cls == COOP_TRACKED);
         __syncwarp();
         // ---- phase 1: 32 lanes per ray
@@ -538,17 +544,19 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, uint32_t* listed_ma
             const double* xs = kr.starts + 3 * __shfl_sync(0xffffffffu, start_index, j);
             const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
             CoopLists L;
-            if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_tracked |= 1u << j; n_handed++; continue; }
+            // a ray that fails a check goes back to the per-thread walker of its kind
+            uint32_t& m_back = rec.e_mid == 0 ? m_listed : m_tracked;
+            if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_back |= 1u << j; n_handed++; continue; }
             double* tEA; int32_t* sEA;
             const int nEA = coop_merge_ea(P, wbase, L, lane, tEA, sEA);
-            if (nEA < 0) { m_tracked |= 1u << j; n_handed++; continue; }     // a list out of order
+            if (nEA < 0) { m_back |= 1u << j; n_handed++; continue; }        // a list out of order
             typename Op::Sink sink = op.begin(ray);
             coop_segments<Op::kEvents>(L, tEA, sEA, nEA, lane, sink);
             op.coop_end(ray, sink, lane, L.nR + L.nE + L.nA);
             n_coop++;
             __syncwarp();              // the lists are reused by the next ray
         }
-        if (lane == 0) { listed_mask[tile] = m_listed; tracked_mask[tile] = m_tracked; }
+        if (lane == 0) { listed_mask[tile] = m_listed; if (in_mask == nullptr) tracked_mask[tile] = m_tracked; }
         if (stats != nullptr && lane == 0) {
             atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));
             atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
@@ -685,6 +693,13 @@ CoopLaunch plan_coop(const sphrt_grid& g, int64_t n_rays)
 
 // SPHRT_WALKER = auto (default) | coop | tracked : which walker takes the ordinary rays.
 // auto: the cooperative walker pays off once a ray meets a few hundred boundaries.
+// SPHRT_COOP_LISTED=0 keeps the sorted-cone-list rays of the per-thread path in pass B (tests)
+bool no_coop_listed()
+{
+    const char* e = getenv("SPHRT_COOP_LISTED");
+    return e != nullptr && strcmp(e, "0") == 0;
+}
+
 bool want_coop(const sphrt_grid& g)
 {
     const char* e = getenv("SPHRT_WALKER");
@@ -766,7 +781,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
             cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
             unsigned long long* tile_counter = counters;
             walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, mask, mask_tracked, tile_counter, stats);
+                *grid, kr, op, cl.P, nullptr, mask, mask_tracked, tile_counter, stats);
             int rc = cuda_status();
             if (rc != SPHRT_OK) return rc;
             if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
@@ -796,6 +811,20 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
                                                                        (int)(smem / sizeof(double)), mask);
     int rc = cuda_status();
     if (rc != SPHRT_OK) return rc;
+    if constexpr (Op::kCoop) {
+        // the rays that need the sorted cone list are a few per cent of the rays but (walked by one
+        // thread each) more than half of a step on the 50^3 grids: walk them cooperatively in
+        // all-cones mode first; pass B keeps what that cannot take (starts on a boundary ...)
+        const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
+        if (cl.ok && !no_coop_listed()) {
+            cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                *grid, kr, op, cl.P, mask, mask_tracked, nullptr, counters, nullptr);
+            rc = cuda_status();
+            if (rc != SPHRT_OK) return rc;
+            return launch_listed(grid, kr, op, mask_tracked, lists, smem, lp, counters + 2, st);
+        }
+    }
     return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
     }
 }
