@@ -100,7 +100,7 @@ __device__ __forceinline__ int coop_bin_cos(const GridView& g, double cosv)
 
 // Start points are shared by whole observations: their classification is cached per lane.
 struct CoopStartCache {
-    int64_t index; bool generic;                   // generic: inside the grid or on a cone / half-plane
+    int64_t index; bool inside, on_boundary;       // inside the outermost shell; on a cone / half-plane
     int se, sa, a_bin;                             // reference states and azimuth bin of the start
 };
 
@@ -117,8 +117,8 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     const double t_in = c.tc - sN, t_out = c.tc + sN;
     if (t_out < 0) return COOP_MISS;                              // the grid lies behind the start
     // Rays whose cone roots lose adjacency (snapped discriminant or leading coefficient,
-    // ray_needs_cone_list) are walked from t = 0 with EVERY cone evaluated and the roots sorted
-    // explicitly ("all-cones mode", e_mid == 0)
+    // ray_needs_cone_list) and rays that start on a boundary are walked from t = 0 with EVERY cone
+    // evaluated and the roots sorted explicitly ("all-cones mode", e_mid == 0)
     const bool listed = ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);
     const int hand_over = listed ? COOP_LISTED : COOP_TRACKED;
     if (!g.wrap) return hand_over;                // partial azimuth range: gap sector logic
@@ -127,13 +127,17 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
         double sph[3];
         coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
         cache.index = start_index;
-        cache.generic = bins[0] != g.nr || near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
-                        near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+        cache.inside = bins[0] != g.nr;
+        cache.on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
+                            near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
         cache.se = st[1]; cache.sa = st[2]; cache.a_bin = bins[2];
     }
-    if (cache.generic) return hand_over;                          // starts inside / on a boundary
+    if (cache.inside) return hand_over;           // starts inside the grid (quirk 1, no entry event)
     if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return hand_over;
-    const bool all_cones = listed;
+    // a start ON a cone or half-plane makes the reference keep or lose the t ~ 0 crossing by
+    // rounding: no shortcut from the geometry of the entry point then, but the all-cones walk from
+    // t = 0 applies the reference's own rule (t >= 0) to the reference's own roots
+    const bool all_cones = listed || cache.on_boundary;
     // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
     int lo = 0, hi = g.nr;
     while (lo < hi) {

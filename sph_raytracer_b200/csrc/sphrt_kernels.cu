@@ -479,7 +479,7 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
     double* recd = reinterpret_cast<double*>(wbase + P.off_rec);
     const int64_t n_tiles = (kr.n + 31) >> 5;
     unsigned long long n_coop = 0, n_handed = 0;
-    CoopStartCache start_cache{-1, true};
+    CoopStartCache start_cache{-1, true, true, 0, 0, 0};
     // the cooperative ranges assume cos(e_b) descends (e_b ascending within [0, pi])
     bool table_ok = true;
     for (int k = threadIdx.x; k < g.ne; k += blockDim.x) table_ok &= g.cos_e()[k] > g.cos_e()[k + 1];
