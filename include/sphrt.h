@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 1
+#define SPHRT_VERSION 2
 
 enum {
     SPHRT_OK = 0,
@@ -68,6 +68,10 @@ typedef struct sphrt_rays {
     int64_t rays_per_start;
     const double *dirs;
     int64_t rays_per_dir;
+    int64_t walker;            /* which kernel walks the ordinary rays: 0 = library's choice,
+                                * 1 = warp-cooperative, 2 = per-thread.  Same results either way;
+                                * the caller may time both once and keep the faster one (the Python
+                                * Operator does).  SPHRT_WALKER in the environment overrides. */
 } sphrt_rays;
 
 /* Bytes of caller-owned scratch the tracing entry points need for this grid and ray count:

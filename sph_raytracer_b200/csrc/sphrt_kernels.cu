@@ -700,12 +700,14 @@ bool no_coop_listed()
     return e != nullptr && strcmp(e, "0") == 0;
 }
 
-bool want_coop(const sphrt_grid& g)
+bool want_coop(const sphrt_grid& g, int64_t hint = 0)
 {
     const char* e = getenv("SPHRT_WALKER");
     if (e != nullptr && strcmp(e, "coop") == 0) return true;
     if (e != nullptr && strcmp(e, "tracked") == 0) return false;
-    return g.nr + g.ne + g.na >= 400;
+    if (hint == 1) return true;
+    if (hint == 2) return false;
+    return g.nr + g.ne + g.na >= 300;
 }
 
 int check_grid(const sphrt_grid* g)
@@ -725,6 +727,7 @@ int check_rays(const sphrt_rays* r)
     if (r == nullptr || r->n_rays < 0) return SPHRT_EINVAL;
     if (r->n_rays > 0 && (!r->starts || !r->dirs || r->rays_per_start < 1 || r->rays_per_dir < 1))
         return SPHRT_EINVAL;
+    if (r->walker < 0 || r->walker > 2) return SPHRT_EINVAL;
     return SPHRT_OK;
 }
 
@@ -777,7 +780,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
 
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
-        if (cl.ok && (force_coop || want_coop(*grid))) {
+        if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
             cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
             unsigned long long* tile_counter = counters;
             walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(

@@ -102,7 +102,7 @@ class _Rays:
         d, self.rays_per_dir = _compact(dirs, self.shape)
         self.starts, self.dirs = s.to(device), d.to(device)
         self.c = _cabi.Rays(self.n, self.starts.data_ptr(), self.rays_per_start,
-                            self.dirs.data_ptr(), self.rays_per_dir)
+                            self.dirs.data_ptr(), self.rays_per_dir, 0)
 
 
 class _LineIntegral(torch.autograd.Function):
@@ -168,6 +168,7 @@ class Operator:
         self._rays = _Rays(geom, self._cdev)
         self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         self._stored = None
+        self._autotune()
         if store_segments:
             self._store(torch.float64 if store_segments is torch.float64 else torch.float32)
         if debug:
@@ -179,6 +180,39 @@ class Operator:
 
     def _scratch(self):
         return torch.empty(max(self._scratch_bytes, 8), dtype=torch.uint8, device=self._cdev)
+
+    def _autotune(self, max_rays=1 << 20):
+        """Pick the kernel for the ordinary rays by measurement: the warp-cooperative and the
+        per-thread walker give the same segments, which one is faster depends on grid size and
+        on how alike neighbouring rays are.  One warm-up and two timed forward passes per
+        kernel over (a prefix of) this operator's own rays; SPHRT_AUTOTUNE=0 keeps the library's
+        size heuristic, SPHRT_WALKER forces a kernel."""
+        import os
+        if os.environ.get("SPHRT_AUTOTUNE", "1") == "0" or os.environ.get("SPHRT_WALKER") or self._rays.n < 4096:
+            return
+        r, t = self._rays, self._tables
+        probe = _cabi.Rays(min(r.n, max_rays), r.starts.data_ptr(), r.rays_per_start,
+                           r.dirs.data_ptr(), r.rays_per_dir, 0)
+        vol = torch.ones(t.nvox, dtype=torch.float32, device=self._cdev)
+        out = torch.empty(probe.n_rays, dtype=torch.float32, device=self._cdev)
+        scratch = self._scratch()
+        best = None
+        with torch.cuda.device(self._cdev):
+            for walker in (1, 2):
+                probe.walker = walker
+                times = []
+                for k in range(3):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    _cabi.check(self._lib.sphrt_forward(t.c, probe, vol.data_ptr(), _cabi.F32, 1, 0,
+                                                        out.data_ptr(), scratch.data_ptr(),
+                                                        scratch.numel(), self._stream()))
+                    b.record()
+                    b.synchronize()
+                    times.append(a.elapsed_time(b))
+                if best is None or min(times[1:]) < best[0]:
+                    best = (min(times[1:]), walker)
+        r.c.walker = best[1]
 
     def _store(self, len_dtype):
         """Trace once and keep the canonical segments (offsets, flat voxel offsets, lengths)."""
@@ -368,6 +402,9 @@ class Operator:
 
     def walker(self):
         """'cooperative' or 'per-thread': the kernel that walks this operator's ordinary rays."""
+        import os
+        if self._rays.c.walker and not os.environ.get("SPHRT_WALKER"):
+            return "cooperative" if self._rays.c.walker == 1 else "per-thread"
         kind = int(self._lib.sphrt_walker_kind(self._tables.c, self._rays.n))
         _cabi.check(min(kind, 0))
         return "cooperative" if kind == 1 else "per-thread"
