@@ -463,15 +463,16 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
 constexpr int kCoopRecDoubles = 6;
 
-template <class Op>
+template <class Op, bool kAllCones>
 __global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
 walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_mask,
                  uint32_t* listed_mask, uint32_t* tracked_mask, unsigned long long* tile_counter,
                  unsigned long long* stats)
 {
-    // in_mask == nullptr: every ray.  Otherwise only the flagged rays (the sorted-cone-list rays
-    // of the per-thread walker, small grids): they are walked in all-cones mode and what is left
-    // over goes to listed_mask again.
+    // kAllCones == false, in_mask == nullptr: every ray; rays that need the all-cones mode or pass B
+    // are flagged in listed_mask.  kAllCones == true: only the rays flagged in in_mask (by the run
+    // before, or by the per-thread walker on small grids), walked in all-cones mode; what is left
+    // over is flagged in listed_mask again (which may be in_mask itself: one warp owns a word).
     extern __shared__ double sm_tables[];
     const GridView g = stage_tables(kg, sm_tables);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -504,7 +505,7 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
             RayConsts c;
             ray_setup(c, x, d);
             CoopRecord rec;
-            cls = coop_plan_ray(g, c, x, P, start_index, start_cache, rec);
+            cls = coop_plan_ray<kAllCones>(g, c, x, P, start_index, start_cache, rec);
             if (!table_ok && cls == COOP_RAY) cls = COOP_TRACKED;
             if (cls == COOP_RAY) {
                 recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
@@ -545,8 +546,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
             const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
             CoopLists L;
             // a ray that fails a check goes back to the per-thread walker of its kind
-            uint32_t& m_back = rec.e_mid == 0 ? m_listed : m_tracked;
-            if (!coop_build(g, P, wbase, rec, x, lane, L)) { m_back |= 1u << j; n_handed++; continue; }
+            uint32_t& m_back = kAllCones ? m_listed : m_tracked;
+            if (!coop_build<kAllCones>(g, P, wbase, rec, x, lane, L)) { m_back |= 1u << j; n_handed++; continue; }
             double* tEA; int32_t* sEA;
             const int nEA = coop_merge_ea(P, wbase, L, lane, tEA, sEA);
             if (nEA < 0) { m_back |= 1u << j; n_handed++; continue; }        // a list out of order
@@ -558,8 +559,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         }
         if (lane == 0) { listed_mask[tile] = m_listed; if (in_mask == nullptr) tracked_mask[tile] = m_tracked; }
         if (stats != nullptr && lane == 0) {
-            atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));
-            atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
+            if (kAllCones) atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));    // left for pass B
+            else atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
         }
     }
     if (stats != nullptr && lane == 0) { atomicAdd(stats + 0, n_coop); atomicAdd(stats + 3, n_handed); }
@@ -774,18 +775,24 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     uint32_t* mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
     void* lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
     const int64_t n_words = (rays->n_rays + 31) / 32;
-    // work hand-out counters: [0] cooperative tiles, [1] masked per-thread pass, [2] listed pass
+    // work hand-out counters: [0] cooperative tiles, [1] masked per-thread pass, [2] listed pass,
+    // [3] cooperative all-cones tiles
     unsigned long long* counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
-    cudaMemsetAsync(counters, 0, 3 * sizeof(unsigned long long), st);
+    cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st);
 
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
-            cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            unsigned long long* tile_counter = counters;
-            walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, nullptr, mask, mask_tracked, tile_counter, stats);
+            cudaFuncSetAttribute(walk_coop_kernel<Op, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            cudaFuncSetAttribute(walk_coop_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            walk_coop_kernel<Op, false><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
             int rc = cuda_status();
+            if (rc != SPHRT_OK) return rc;
+            // the rays that need every cone evaluated and sorted (about 1 %), in place on their mask
+            walk_coop_kernel<Op, true><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                *grid, kr, op, cl.P, mask, mask, mask_tracked, counters + 3, stats);
+            rc = cuda_status();
             if (rc != SPHRT_OK) return rc;
             if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
             else {
@@ -820,12 +827,11 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
         // all-cones mode first; pass B keeps what that cannot take (starts on a boundary ...)
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && !no_coop_listed()) {
-            cudaFuncSetAttribute(walk_coop_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            walk_coop_kernel<Op><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, mask, mask_tracked, nullptr, counters, nullptr);
+            cudaFuncSetAttribute(walk_coop_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            walk_coop_kernel<Op, true><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                *grid, kr, op, cl.P, mask, mask, nullptr, counters + 3, nullptr);
             rc = cuda_status();
             if (rc != SPHRT_OK) return rc;
-            return launch_listed(grid, kr, op, mask_tracked, lists, smem, lp, counters + 2, st);
         }
     }
     return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
