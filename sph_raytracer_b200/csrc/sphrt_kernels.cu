@@ -463,6 +463,44 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
 constexpr int kCoopRecDoubles = 6;
 
+// phase 0 of the cooperative walker for one ray: load, set up, classify, plan; the float64 part of
+// the record goes to shared memory ([field][lane]), the integer part comes back in registers
+struct Phase0Result { int cls; int ri[6]; int64_t start_index; };
+
+template <bool kAllCones>
+__device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, const KRays& kr, const CoopPlan& P,
+                                                         int64_t i, int lane, double* recd,
+                                                         CoopStartCache* cache, bool table_ok)
+{
+    Phase0Result r;
+    r.ri[0] = r.ri[1] = r.ri[2] = r.ri[3] = r.ri[4] = r.ri[5] = 0;
+    double x[3], d[3];
+    load_ray(kr, i, x, d);
+    r.start_index = i / kr.rps;
+    RayConsts c;
+    ray_setup(c, x, d);
+    CoopRecord rec;
+    r.cls = coop_plan_ray<kAllCones>(g, c, x, P, r.start_index, *cache, rec);
+    if (!table_ok && r.cls == COOP_RAY) r.cls = kAllCones ? COOP_LISTED : COOP_TRACKED;
+    if (r.cls == COOP_RAY) {
+        recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
+        recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
+        recd[5 * 32 + lane] = rec.t_turn;
+        r.ri[0] = rec.imin | (rec.e_mid << 16);
+        r.ri[1] = rec.e_first; r.ri[2] = rec.e_count * rec.e_step;
+        r.ri[3] = rec.a_first; r.ri[4] = rec.a_count * rec.a_dir;
+        r.ri[5] = (rec.se0 & 0xffff) | (rec.sa0 << 16);
+    }
+    return r;
+}
+
+template <bool kAllCones>
+__device__ __noinline__ Phase0Result coop_phase0(GridView g, KRays kr, CoopPlan P, int64_t i, int lane,
+                                                 double* recd, CoopStartCache* cache, bool table_ok)
+{
+    return coop_phase0_body<kAllCones>(g, kr, P, i, lane, recd, cache, table_ok);
+}
+
 template <class Op, bool kAllCones>
 __global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
 walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_mask,
@@ -499,23 +537,13 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         const uint32_t sel = in_mask != nullptr ? __ldg(in_mask + tile) : 0xffffffffu;
         if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
         if (i < kr.n && ((sel >> lane) & 1u)) {
-            double x[3], d[3];
-            load_ray(kr, i, x, d);
-            start_index = i / kr.rps;
-            RayConsts c;
-            ray_setup(c, x, d);
-            CoopRecord rec;
-            cls = coop_plan_ray<kAllCones>(g, c, x, P, start_index, start_cache, rec);
-            if (!table_ok && cls == COOP_RAY) cls = COOP_TRACKED;
-            if (cls == COOP_RAY) {
-                recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
-                recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
-                recd[5 * 32 + lane] = rec.t_turn;
-                ri0 = rec.imin | (rec.e_mid << 16);
-                ri1 = rec.e_first; ri2 = rec.e_count * rec.e_step;
-                ri3 = rec.a_first; ri4 = rec.a_count * rec.a_dir;
-                ri5 = (rec.se0 & 0xffff) | (rec.sa0 << 16);
-            }
+#ifdef SPHRT_PHASE0_NOINLINE
+            const Phase0Result r0 = coop_phase0<kAllCones>(g, kr, P, i, lane, recd, &start_cache, table_ok);
+#else
+            const Phase0Result r0 = coop_phase0_body<kAllCones>(g, kr, P, i, lane, recd, &start_cache, table_ok);
+#endif
+            cls = r0.cls; start_index = r0.start_index;
+            ri0 = r0.ri[0]; ri1 = r0.ri[1]; ri2 = r0.ri[2]; ri3 = r0.ri[3]; ri4 = r0.ri[4]; ri5 = r0.ri[5];
         }
         if (cls == COOP_MISS && i < kr.n && ((sel >> lane) & 1u)) {   // never enters the grid: empty result
             typename Op::Sink none = op.begin(i);
