@@ -456,7 +456,7 @@ __device__ __forceinline__ int coop_corank(const double* X, int nX, const double
 {
     int lo = g - nY > 0 ? g - nY : 0, hi = g < nX ? g : nX;
 #ifdef SPHRT_CORANK_UNROLL
-#pragma unroll SPHRT_CORANK_UNROLL
+#pragma unroll 4
 #endif
     for (int s = 0; s < steps; s++) {
         const int mid = (lo + hi) >> 1;
