@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 2
+#define SPHRT_VERSION 3
 
 enum {
     SPHRT_OK = 0,
@@ -68,6 +68,16 @@ typedef struct sphrt_rays {
     int64_t rays_per_start;
     const double *dirs;
     int64_t rays_per_dir;
+    const int32_t *start_cells;/* optional (may be NULL): for each row of `starts`, 8 int32 --
+                                * the reference's find_starts() of that point evaluated ON THE HOST
+                                * with the reference's own library (torch: cart2sph + searchsorted,
+                                * raytracer.py:555-578, 605-644): geometric bins r,e,a (searchsorted
+                                * - 1, a value equal to the last boundary counted into the last bin),
+                                * states r,e,a (bin n -> -1), 1 if the point lies within 1e-9 of a
+                                * cone or half-plane, 0 (pad).  A start that sits on a boundary to
+                                * the last bit is binned by the last bit of atan2, which differs
+                                * between libms; with this table the kernels bin it like the
+                                * reference does.  NULL: binned in the kernel (CUDA atan2). */
     int64_t walker;            /* which kernel walks the ordinary rays: 0 = library's choice,
                                 * 1 = warp-cooperative, 2 = per-thread.  Same results either way;
                                 * the caller may time both once and keep the faster one (the Python

@@ -28,7 +28,8 @@ class Grid(ctypes.Structure):
 class Rays(ctypes.Structure):
     """struct sphrt_rays"""
     _fields_ = [("n_rays", c_int64), ("starts", c_void_p), ("rays_per_start", c_int64),
-                ("dirs", c_void_p), ("rays_per_dir", c_int64), ("walker", c_int64)]
+                ("dirs", c_void_p), ("rays_per_dir", c_int64), ("start_cells", c_void_p),
+                ("walker", c_int64)]
 
 
 class SphrtError(RuntimeError):

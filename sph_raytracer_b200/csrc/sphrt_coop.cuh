@@ -111,7 +111,7 @@ struct CoopStartCache {
 template <bool kAllCones>
 __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
                                              const CoopPlan& P, int64_t start_index,
-                                             CoopStartCache& cache, CoopRecord& rec)
+                                             const int32_t* cells, CoopStartCache& cache, CoopRecord& rec)
 {
     // a ray that never reaches the outermost shell has no segment, whatever else holds for it
     if (c.dperp2 != c.dperp2) return COOP_MISS;                   // no radial root at all
@@ -127,18 +127,32 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     const bool listed = ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);
     // (the all-cones run only sees flagged rays and has one way out: pass B, which takes any ray)
     const int hand_over = (kAllCones || listed) ? COOP_LISTED : COOP_TRACKED;
-    if (!g.wrap) return hand_over;                // partial azimuth range: gap sector logic
     if (start_index != cache.index) {
         int bins[3], st[3];
-        double sph[3];
-        coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
+        bool on_b;
+        if (cells != nullptr) {
+            // the reference's own binning of the start point, evaluated on the host (sphrt.h)
+            const int32_t* p = cells + 8 * start_index;
+            bins[0] = __ldg(p); bins[1] = __ldg(p + 1); bins[2] = __ldg(p + 2);
+            st[0] = __ldg(p + 3); st[1] = __ldg(p + 4); st[2] = __ldg(p + 5);
+            on_b = __ldg(p + 6) != 0;
+        } else {
+            double sph[3];
+            coop_locate_point(g, x[0], x[1], x[2], bins, st, sph);
+            on_b = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
+                   near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+        }
         cache.index = start_index;
         cache.inside = bins[0] != g.nr;
-        cache.on_boundary = near_boundary(g.e_b(), g.ne, bins[1], sph[1], 1e-9) ||
-                            near_boundary(g.a_b(), g.na, bins[2], sph[2], 1e-9);
+        cache.on_boundary = on_b;
         cache.se = st[1]; cache.sa = st[2]; cache.a_bin = bins[2];
     }
-    if (cache.inside) return hand_over;           // starts inside the grid (quirk 1, no entry event)
+    // partial azimuth range (gap sector logic): per-thread walkers; the bin tracker only when the
+    // start is not on a boundary
+    if (!g.wrap) return cache.on_boundary ? COOP_LISTED : hand_over;
+    // starts inside the grid (quirk 1, no entry event): per-thread walkers; the bin tracker only
+    // when the start is not on a boundary
+    if (cache.inside) return cache.on_boundary ? COOP_LISTED : hand_over;
     if (!(t_in >= 0) || !(t_out < SPHRT_INF)) return hand_over;
     // a start ON a cone or half-plane makes the reference keep or lose the t ~ 0 crossing by
     // rounding: no shortcut from the geometry of the entry point then, but the all-cones walk from

@@ -114,7 +114,20 @@ struct FastAzimuth {
         eval(g, c, plane_of(g, sector, +1), t_now, false, tb, gb);
         if (ta <= tb) { t_next = ta; geo_next = ga; dir = -1; t_alt = tb; geo_alt = gb; }
         else          { t_next = tb; geo_next = gb; dir = +1; t_alt = ta; geo_alt = ga; }
-        if (t_next == SPHRT_INF) dir = 0;
+        if (t_next == SPHRT_INF) {
+            // No root ahead in either bounding plane.  Usually the ray never leaves this sector;
+            // but a start ON a half-plane whose t ~ 0 root came out negative is geometrically in
+            // the neighbouring sector already (the reference ignores that root and meets the
+            // next plane with the start bin still in place): probe the planes beyond.
+            const int nsec = n_sectors(g);
+            const int sd = sector == 0 ? nsec - 1 : sector - 1, su = sector == nsec - 1 ? 0 : sector + 1;
+            eval(g, c, plane_of(g, sd, -1), t_now, false, ta, ga);
+            eval(g, c, plane_of(g, su, +1), t_now, false, tb, gb);
+            if (ta <= tb) { t_next = ta; geo_next = ga; dir = -1; sector = sd; }
+            else          { t_next = tb; geo_next = gb; dir = +1; sector = su; }
+            t_alt = SPHRT_INF;
+            if (t_next == SPHRT_INF) dir = 0;
+        }
     }
     SPHRT_HD bool next(const GridView& g, const RayConsts& c, double& t, int& region)
     {
@@ -221,7 +234,7 @@ struct Ring {
 // part (lanes without a ray pass active = false); on the host it is the identity.
 template <int Q, int STRIDE, class Sink, class Any>
 SPHRT_HD void walk_ray_fast(const GridView& g, const RayConsts& c, const double x[3], bool active,
-                            double* qt, int* qr, Sink& sink, Any any)
+                            double* qt, int* qr, Sink& sink, Any any, const StartCell* pre = nullptr)
 {
     FastRadial rs; FastElevation es; FastAzimuth as;
     Ring<Q, STRIDE> qR, qE, qA;
@@ -237,7 +250,9 @@ SPHRT_HD void walk_ray_fast(const GridView& g, const RayConsts& c, const double 
     if (active) {
         int bins[3], st[3];
         double sph[3];
-        start_voxel(g, x, bins, st, sph);
+        if (pre != nullptr) {
+            for (int k = 0; k < 3; k++) { bins[k] = pre->bins[k]; st[k] = pre->st[k]; sph[k] = pre->sph[k]; }
+        } else start_voxel(g, x, bins, st, sph);
         rs.init(g, c);
         double t0; int r0;
         const bool has_r = rs.next(g, c, t0, r0);

@@ -50,7 +50,23 @@ struct KRays {
     int64_t n;
     const double* starts; int64_t rps;
     const double* dirs; int64_t rpd;
+    const int32_t* cells;          // host-evaluated find_starts of every start row (may be null)
 };
+
+// Start voxel of ray i: from the caller's table (the reference's own binning) or, without one,
+// evaluated here.
+__device__ __forceinline__ StartCell ray_start_cell(const KRays& kr, int64_t i, const GridView& g,
+                                                    const double x[3])
+{
+    if (kr.cells == nullptr) return start_cell(g, x);
+    const int32_t* p = kr.cells + 8 * (i / kr.rps);
+    StartCell s;
+    s.bins[0] = __ldg(p); s.bins[1] = __ldg(p + 1); s.bins[2] = __ldg(p + 2);
+    s.st[0] = __ldg(p + 3); s.st[1] = __ldg(p + 4); s.st[2] = __ldg(p + 5);
+    s.on_boundary = __ldg(p + 6) != 0;
+    s.sph[0] = s.sph[1] = s.sph[2] = 0.0;          // only used for on_boundary, which is given
+    return s;
+}
 
 __host__ __device__ inline int64_t table_doubles(const sphrt_grid& kg)
 {
@@ -363,17 +379,24 @@ walk_tracked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem, uint
     bool active = i < kr.n;
     double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
     RayConsts c;
+    StartCell cell;
     if (active) {
         load_ray(kr, i, x, d);
         ray_setup(c, x, d);
         active = !ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);     // pass B takes those
+        if (active) {
+            // ... and the rays that start ON a cone or half-plane: the bin trackers are not exact
+            // there (tools/fuzz.py), the sorted-list walkers apply the reference's own rule
+            cell = ray_start_cell(kr, i, g, x);
+            active = !cell.on_boundary;
+        }
     }
     // one bit per ray: the rays pass B has to walk (ray index and warp are 32-aligned)
     const uint32_t listed = __ballot_sync(0xffffffffu, i < kr.n && !active);
     if ((threadIdx.x & 31) == 0 && i < kr.n) listed_mask[i >> 5] = listed;
     const bool mine = active;
     typename Op::Sink sink = op.begin(mine ? i : 0);
-    walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+    walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny(), &cell);
     if (mine) op.end(i, sink);
 }
 
@@ -448,9 +471,10 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
                      [&](int64_t i, bool active) {
         double x[3] = {0, 0, 0}, d[3] = {0, 0, 1};
         RayConsts c;
-        if (active) { load_ray(kr, i, x, d); ray_setup(c, x, d); }
+        StartCell cell;
+        if (active) { load_ray(kr, i, x, d); ray_setup(c, x, d); cell = ray_start_cell(kr, i, g, x); }
         typename Op::Sink sink = op.begin(active ? i : 0);
-        walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny());
+        walk_ray_fast<kQueue, kBlock>(g, c, x, active, qt, qr, sink, WarpAny(), &cell);
         if (active) op.end(i, sink);
     });
 }
@@ -480,7 +504,7 @@ __device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, cons
     RayConsts c;
     ray_setup(c, x, d);
     CoopRecord rec;
-    r.cls = coop_plan_ray<kAllCones>(g, c, x, P, r.start_index, *cache, rec);
+    r.cls = coop_plan_ray<kAllCones>(g, c, x, P, r.start_index, kr.cells, *cache, rec);
     if (!table_ok && r.cls == COOP_RAY) r.cls = kAllCones ? COOP_LISTED : COOP_TRACKED;
     if (r.cls == COOP_RAY) {
         recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
@@ -625,7 +649,8 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, 
         RayConsts c;
         ray_setup(c, x, d);
         typename Op::Sink sink = op.begin(i);
-        walk_ray<true>(g, c, x, list, sink);
+        const StartCell cell = ray_start_cell(kr, i, g, x);
+        walk_ray<true>(g, c, x, list, sink, &cell);
         op.end(i, sink);
     });
 }
@@ -795,7 +820,8 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     if (rays->n_rays == 0) return SPHRT_OK;
     if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
     cudaStream_t st = (cudaStream_t)stream;
-    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir};
+    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
+                   rays->start_cells};
     const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
     const size_t smem_a = smem + kQueueBytes;
     const ListPlan lp = plan_lists(*grid, rays->n_rays);

@@ -519,6 +519,17 @@ struct AzimuthStream {
         Event b = eval(g, c, upper_plane(g, sector), 0.0);
         t_lo = a.t; r_lo = pack_rg(a);
         t_hi = b.t; r_hi = pack_rg(b);
+        if (t_lo == SPHRT_INF && t_hi == SPHRT_INF) {
+            // No root ahead in either bounding plane: a start ON a half-plane whose t ~ 0 root came
+            // out negative is geometrically in the neighbouring sector already (the reference
+            // ignores that root and meets the next plane with the start bin still in place).
+            const int nsec = n_sectors(g);
+            const int sd = sector == 0 ? nsec - 1 : sector - 1, su = sector == nsec - 1 ? 0 : sector + 1;
+            a = eval(g, c, lower_plane(g, sd), 0.0);
+            b = eval(g, c, upper_plane(g, su), 0.0);
+            if (a.t <= b.t) { if (a.t < SPHRT_INF) { sector = sd; t_lo = a.t; r_lo = pack_rg(a); } }
+            else            { sector = su; t_hi = b.t; r_hi = pack_rg(b); }
+        }
         peek();
     }
     SPHRT_HD void advance(const GridView& g, const RayConsts& c)
@@ -586,12 +597,30 @@ SPHRT_HD void start_voxel(const GridView& g, const double x[3], int bins[3], int
     if (sph) { sph[0] = r; sph[1] = e; sph[2] = a; }
 }
 
+// Start voxel of a ray with the classification the kernels need: geometric bins, reference
+// states, spherical coordinates, and whether the point sits on a cone or half-plane (the
+// reference then keeps or loses the t ~ 0 crossing by rounding).
+struct StartCell {
+    int bins[3], st[3];
+    double sph[3];
+    bool on_boundary;
+};
+
 // true if v lies within `tol` of one of the boundaries of its bin
 SPHRT_HD bool near_boundary(const double* b, int n, int bin, double v, double tol)
 {
     const int lo = bin < 0 ? 0 : (bin > n ? n : bin);
     const int hi = bin + 1 > n ? n : (bin + 1 < 0 ? 0 : bin + 1);
     return fabs(v - b[lo]) < tol || fabs(v - b[hi]) < tol;
+}
+
+SPHRT_HD StartCell start_cell(const GridView& g, const double x[3])
+{
+    StartCell s;
+    start_voxel(g, x, s.bins, s.st, s.sph);
+    s.on_boundary = near_boundary(g.e_b(), g.ne, s.bins[1], s.sph[1], 1e-9) ||
+                    near_boundary(g.a_b(), g.na, s.bins[2], s.sph[2], 1e-9);
+    return s;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -603,10 +632,11 @@ SPHRT_HD bool near_boundary(const double* b, int n, int bin, double v, double to
 // ray_needs_cone_list(c, g.c2_sorted(), g.n_c2) for the ray; `c` comes from ray_setup().
 template <bool kList, class Sink>
 SPHRT_HD void walk_ray(const GridView& g, const RayConsts& c, const double x[3],
-                       const ConeList& scratch, Sink& sink)
+                       const ConeList& scratch, Sink& sink, const StartCell* pre = nullptr)
 {
     int bins[3], st[3];
-    start_voxel(g, x, bins, st);
+    if (pre != nullptr) { for (int k = 0; k < 3; k++) { bins[k] = pre->bins[k]; st[k] = pre->st[k]; } }
+    else start_voxel(g, x, bins, st);
 
     RadialStream rs;
     rs.init(g, c);

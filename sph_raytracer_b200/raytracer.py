@@ -54,6 +54,7 @@ class _GridTables:
         r_b = torch.asarray(grid.r_b, dtype=torch.float64).cpu().reshape(-1)
         e_b = torch.asarray(grid.e_b, dtype=torch.float64).cpu().reshape(-1)
         a_b = torch.asarray(grid.a_b, dtype=torch.float64).cpu().reshape(-1)
+        self.r_b, self.e_b, self.a_b = r_b, e_b, a_b
         self.nr, self.ne, self.na = len(r_b) - 1, len(e_b) - 1, len(a_b) - 1
         if min(self.nr, self.ne, self.na) < 1:
             raise ValueError("grid needs at least one voxel along every axis")
@@ -85,10 +86,35 @@ def _compact(t, full_shape):
     return t.broadcast_to(tuple(full_shape) + (3,)).reshape(-1, 3).contiguous(), 1
 
 
+def _start_cells(r_b, e_b, a_b, starts):
+    """The reference's binning of start points (cart2sph + find_starts, raytracer.py:555-578,
+    605-644) evaluated on the host with torch -- the same library the reference uses, so that a
+    start sitting on a cone or half-plane to the last bit lands in the bin the reference puts it
+    in (atan2 differs in the last ulp between libms).  Returns int32
+    (m, 8): geometric bins r,e,a, reference states r,e,a, on-boundary flag, 0."""
+    x, y, z = starts.unbind(-1)
+    xy_sq = x ** 2 + y ** 2
+    sph = (torch.sqrt(xy_sq + z ** 2), torch.arctan2(torch.sqrt(xy_sq), z), torch.arctan2(y, x))
+    cells = torch.zeros((starts.shape[0], 8), dtype=torch.int32)
+    near = torch.zeros(starts.shape[0], dtype=torch.bool)
+    for k, (b, v) in enumerate(zip((r_b, e_b, a_b), sph)):
+        n = len(b) - 1
+        v = v.contiguous()
+        bins = torch.searchsorted(b, v, right=True) - 1
+        bins = torch.where(v == b[-1], n - 1, bins)
+        cells[:, k] = bins
+        cells[:, 3 + k] = torch.where(bins == n, -1, bins)
+        if k > 0:      # within 1e-9 of a boundary of its elevation / azimuth bin
+            lo, hi = bins.clamp(0, n), (bins + 1).clamp(0, n)
+            near |= ((v - b[lo]).abs() < 1e-9) | ((v - b[hi]).abs() < 1e-9)
+    cells[:, 6] = near.to(torch.int32)
+    return cells
+
+
 class _Rays:
     """Ray origins and directions of a view geometry on the GPU (float64)."""
 
-    def __init__(self, geom, device):
+    def __init__(self, geom, device, tables=None):
         starts = torch.asarray(geom.ray_starts, dtype=torch.float64)
         dirs = torch.asarray(geom.rays, dtype=torch.float64)
         # the reference broadcasts the smaller of the two to the larger (raytracer.py:77-80)
@@ -101,8 +127,12 @@ class _Rays:
         s, self.rays_per_start = _compact(starts, self.shape)
         d, self.rays_per_dir = _compact(dirs, self.shape)
         self.starts, self.dirs = s.to(device), d.to(device)
+        self.cells = None
+        if tables is not None:
+            self.cells = _start_cells(tables.r_b, tables.e_b, tables.a_b, s.cpu()).to(device)
         self.c = _cabi.Rays(self.n, self.starts.data_ptr(), self.rays_per_start,
-                            self.dirs.data_ptr(), self.rays_per_dir, 0)
+                            self.dirs.data_ptr(), self.rays_per_dir,
+                            self.cells.data_ptr() if self.cells is not None else None, 0)
 
 
 class _LineIntegral(torch.autograd.Function):
@@ -165,7 +195,7 @@ class Operator:
         self._lib = _cabi.load()
         self._cdev = _compute_device(device)
         self._tables = _GridTables(grid, self._cdev)
-        self._rays = _Rays(geom, self._cdev)
+        self._rays = _Rays(geom, self._cdev, self._tables)
         self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         self._stored = None
         self._autotune()
@@ -192,7 +222,7 @@ class Operator:
             return
         r, t = self._rays, self._tables
         probe = _cabi.Rays(min(r.n, max_rays), r.starts.data_ptr(), r.rays_per_start,
-                           r.dirs.data_ptr(), r.rays_per_dir, 0)
+                           r.dirs.data_ptr(), r.rays_per_dir, r.c.start_cells, 0)
         vol = torch.ones(t.nvox, dtype=torch.float32, device=self._cdev)
         out = torch.empty(probe.n_rays, dtype=torch.float32, device=self._cdev)
         scratch = self._scratch()

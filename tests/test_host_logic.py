@@ -27,11 +27,11 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib = _cabi.load()
-    assert lib.sphrt_version() == 2
+    assert lib.sphrt_version() == 3
     assert lib.sphrt_error_string(-3).decode().startswith("scratch")
     # argument validation happens before any CUDA call
     g = _cabi.Grid(0, 1, 1, 0, *([0] * 7))
-    r = _cabi.Rays(0, 0, 1, 0, 1, 0)
+    r = _cabi.Rays(0, 0, 1, 0, 1, None, 0)
     assert lib.sphrt_forward(g, r, 0, 0, 1, 0, 0, 0, 0, 0) == -1
     with pytest.raises(_cabi.SphrtError):
         _cabi.check(-1)

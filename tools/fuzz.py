@@ -1,0 +1,99 @@
+"""Differential fuzzing against the CPU oracle: random grids, rays of several kinds (aimed from
+outside, starting inside, starting exactly on grid planes / cones / axes, axis-parallel), every ray
+compared through BOTH GPU walkers' integrals (float64) with the oracle's, plus canonical sequences
+of the per-thread walker.  Usage: fuzz.py [n_grids] [rays_per_kind] [seed]"""
+import os, sys, math, numpy as np, torch
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import sph_raytracer_b200 as S
+from oracle import oracle as O
+
+
+def run(n_grids=12, n=3000, seed=0, verbose=True):
+    rng = np.random.default_rng(seed)
+    g = torch.Generator().manual_seed(seed)
+    tot_bad = 0
+    for k in range(n_grids):
+        shape = tuple(int(v) for v in rng.integers(3, 70, 3))
+        r0 = float(rng.choice([0.0, 0.3, 1.0])); r1 = r0 + float(rng.uniform(0.5, 4))
+        kw = dict(size_r=(r0, r1))
+        if rng.random() < 0.3 and r0 > 0: kw["spacing"] = "log"
+        if rng.random() < 0.25: kw["size_e"] = (float(rng.uniform(0, 0.6)), float(rng.uniform(2.4, math.pi)))
+        if rng.random() < 0.2: kw["size_a"] = (float(rng.uniform(-3, -2)), float(rng.uniform(2, 3)))
+        grid = S.SphericalGrid(shape, **kw)
+        R = r1
+        def unit(m):
+            v = torch.randn(m, 3, generator=g, dtype=torch.float64); return v / v.norm(dim=-1, keepdim=True)
+        xs, ds = [], []
+        # aimed from outside
+        x = unit(n) * (R * (1.5 + 3 * torch.rand(n, 1, generator=g, dtype=torch.float64))); xs.append(x); ds.append(-x + 0.6 * R * torch.randn(n, 3, generator=g, dtype=torch.float64))
+        # starting inside
+        x = unit(n) * (R * torch.rand(n, 1, generator=g, dtype=torch.float64)); xs.append(x); ds.append(torch.randn(n, 3, generator=g, dtype=torch.float64))
+        # starts on axes / grid planes (x = 0, y = 0, z = 0, azimuth of a grid plane), outside
+        x = unit(n) * (R * 2.5); x[: n // 4, 0] = 0; x[n // 4: n // 2, 1] = 0; x[n // 2: 3 * n // 4, 2] = 0
+        a = grid.a_b[torch.randint(0, len(grid.a_b), (n - 3 * n // 4,), generator=g)]
+        rho = R * 2.5
+        x[3 * n // 4:, 0] = rho * torch.cos(a); x[3 * n // 4:, 1] = rho * torch.sin(a)
+        xs.append(x); ds.append(-x + 0.5 * R * torch.randn(n, 3, generator=g, dtype=torch.float64))
+        # starts inside the grid on grid planes / cones (and on the axes)
+        x = unit(n) * (R * (0.2 + 0.7 * torch.rand(n, 1, generator=g, dtype=torch.float64)))
+        a = grid.a_b[torch.randint(0, len(grid.a_b), (n // 2,), generator=g)]
+        rho = (x[: n // 2, 0] ** 2 + x[: n // 2, 1] ** 2).sqrt()
+        x[: n // 2, 0] = rho * torch.cos(a); x[: n // 2, 1] = rho * torch.sin(a)
+        e = grid.e_b[torch.randint(0, len(grid.e_b), (n - n // 2,), generator=g)]
+        rr = x[n // 2:].norm(dim=-1); az = torch.atan2(x[n // 2:, 1], x[n // 2:, 0])
+        x[n // 2:, 0] = rr * torch.sin(e) * torch.cos(az); x[n // 2:, 1] = rr * torch.sin(e) * torch.sin(az); x[n // 2:, 2] = rr * torch.cos(e)
+        xs.append(x); ds.append(torch.randn(n, 3, generator=g, dtype=torch.float64))
+        # axis-parallel rays
+        x = unit(n) * (R * 2); d = torch.zeros(n, 3, dtype=torch.float64); d[torch.arange(n), torch.randint(0, 3, (n,), generator=g)] = 1.0
+        d = d * torch.sign(-(x * d).sum(-1, keepdim=True)); xs.append(x); ds.append(d)
+        xs, ds = torch.cat(xs), torch.cat(ds)
+        geom = S.ViewGeom(xs, ds)
+        og = O.OracleGrid(grid)
+        x_, d_, _ = O.broadcast_rays(geom.ray_starts, geom.rays)
+        regs, lens = O.trace(og, x_, d_)
+        # oracle-stable rays: same canonical sequence under a 4e-16 relative perturbation of the directions
+        regs2, lens2 = O.trace(og, x_, d_ * (1 + 4e-16 * rng.standard_normal(d_.shape)))
+        ms = og.K
+        v0, s0, c0 = O.canonical(og, regs, lens, max_seg=ms)
+        v2, s2, c2 = O.canonical(og, regs2, lens2, max_seg=ms)
+        idx = np.arange(ms)[None, :] < c0[:, None]
+        stable = (c0 == c2) & ((v0 == v2).all(-1) | ~idx).all(-1)
+        # starts that sit on a boundary to the last bit are binned by the last bit of atan2: the product
+        # follows torch (the reference's library), the C oracle follows glibc; leave out the few rays
+        # where those two disagree
+        from sph_raytracer_b200.raytracer import _start_cells
+        cells = _start_cells(grid.r_b.double(), grid.e_b.double(), grid.a_b.double(), xs).numpy()
+        fs_or = np.asarray(O.find_starts(og, x_)).reshape(3, -1)
+        libm = (cells[:, 3:6].T != fs_or).any(0)
+        stable &= ~libm
+        # a start ON the Z axis has no azimuth: as ill-defined in the reference as a ray through it
+        stable &= ~((xs[:, 0] == 0) & (xs[:, 1] == 0)).numpy()
+        dens = rng.random(tuple(grid.shape))
+        want = O.forward(og, regs, lens, dens)[0]
+        op = S.Operator(grid, geom)
+        vox, sl, cnt = op.segments(ms)
+        v1 = vox.reshape(-1, ms, 3).cpu().numpy(); s1 = sl.reshape(-1, ms).cpu().numpy(); c1 = cnt.reshape(-1).cpu().numpy()
+        okseq = (c0 == c1) & ((v0 == v1).all(-1) | ~idx).all(-1) & (np.isclose(s0, s1, rtol=1e-9, atol=1e-12) | ~idx).all(-1)
+        xd = torch.from_numpy(dens).cuda()
+        res = {}
+        for mode in ("tracked", "coop"):
+            os.environ["SPHRT_WALKER"] = mode
+            res[mode] = op._apply_forward(xd).cpu().numpy()
+        os.environ.pop("SPHRT_WALKER")
+        tol = 1e-9 * np.maximum(1.0, np.abs(want))
+        bad_t = stable & (np.abs(res["tracked"] - want) > tol)
+        bad_c = stable & (np.abs(res["coop"] - want) > tol)
+        bad_s = stable & ~okseq
+        stats = op.events(max_ev=8)[3]
+        nb = int(bad_t.sum() + bad_c.sum() + bad_s.sum()); tot_bad += nb
+        if verbose or nb: print(f"grid {shape} {kw}: rays {len(want)} libm-dependent starts {int(libm.sum())} stable {int(stable.sum())} coop-stats {stats}  bad: seq {int(bad_s.sum())} fwd per-thread {int(bad_t.sum())} fwd coop {int(bad_c.sum())}"
+              + (f"  first {np.where(bad_t | bad_c | bad_s)[0][:5].tolist()}" if nb else ""), flush=True)
+
+    return tot_bad
+
+
+if __name__ == "__main__":
+    a = [int(v) for v in sys.argv[1:]]
+    total = run(*a)
+    print("TOTAL BAD", total)
