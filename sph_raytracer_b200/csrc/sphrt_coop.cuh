@@ -104,11 +104,14 @@ struct CoopStartCache {
     int se, sa, a_bin;                             // reference states and azimuth bin of the start
 };
 
-// kAllCones selects which of the two kinds of ray this instantiation takes (the other kind is
-// handed over as COOP_LISTED): the kernel runs once without and once with it, so that the rare
-// all-cones code stays out of the main kernel's instruction stream (inlined into one kernel it
-// cost the forward pass 11 %).
-template <bool kAllCones>
+// kMode selects which kinds of ray this instantiation takes (the other kind is handed over as
+// COOP_LISTED).  Large problems run the kernel twice, once per kind, so that the rare all-cones
+// code stays out of the main kernel's instruction stream (inlined into one kernel it cost the
+// config-5 forward pass 11 %); small ones run it once for both (a second launch costs them more).
+// kMode: COOP_ORDINARY (hand the all-cones rays over), COOP_ALLCONES (only those), COOP_BOTH.
+enum { COOP_ORDINARY = 0, COOP_ALLCONES = 1, COOP_BOTH = 2 };
+
+template <int kMode>
 __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
                                              const CoopPlan& P, int64_t start_index,
                                              const int32_t* cells, CoopStartCache& cache, CoopRecord& rec)
@@ -126,7 +129,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     // evaluated and the roots sorted explicitly ("all-cones mode", e_mid == 0)
     const bool listed = ray_needs_cone_list(c, g.c2_sorted(), g.n_c2);
     // (the all-cones run only sees flagged rays and has one way out: pass B, which takes any ray)
-    const int hand_over = (kAllCones || listed) ? COOP_LISTED : COOP_TRACKED;
+    const int hand_over = (kMode == COOP_ALLCONES || listed) ? COOP_LISTED : COOP_TRACKED;
     if (start_index != cache.index) {
         int bins[3], st[3];
         bool on_b;
@@ -158,7 +161,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     // rounding: no shortcut from the geometry of the entry point then, but the all-cones walk from
     // t = 0 applies the reference's own rule (t >= 0) to the reference's own roots
     const bool all_cones = listed || cache.on_boundary;
-    if (all_cones != kAllCones) return COOP_LISTED;   // the other instantiation's (or pass B's) ray
+    if (kMode != COOP_BOTH && all_cones != (kMode == COOP_ALLCONES)) return COOP_LISTED;   // the other run's ray
     // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
     int lo = 0, hi = g.nr;
     while (lo < hi) {
@@ -174,7 +177,7 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     int qs_a;
     const int qb_a = locate(g.a_b(), g.na, (double)atan2f((float)q[1], (float)q[0]), &qs_a);
     int a_bin_in;
-    if constexpr (kAllCones) {
+    if (kMode != COOP_ORDINARY && all_cones) {
         // walk from the start point: its states, all cones, planes from its sector
         rec.se0 = cache.se; rec.sa0 = cache.sa; a_bin_in = cache.a_bin;
         rec.e_first = 0; rec.e_count = g.ne + 1; rec.e_step = 1; rec.t_turn = -SPHRT_INF; rec.e_mid = 0;
@@ -246,7 +249,7 @@ struct CoopLists {
 
 // Build the three sorted lists of ray `rec`.  Returns false if a structural assumption did not
 // hold (the ray then goes to the per-thread walker).  All lanes of the warp call this.
-template <bool kAllCones>
+template <int kMode>
 __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P, char* wbase,
                                            const CoopRecord& rec, const double x[3], int lane,
                                            CoopLists& L)
@@ -304,7 +307,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
 #endif
     if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
-    constexpr bool all_cones = kAllCones;
+    const bool all_cones = kMode == COOP_BOTH ? rec.e_mid == 0 : kMode == COOP_ALLCONES;
     // events are kept from the entry point on, or from the start point in all-cones mode
     const double t_in = all_cones ? 0.0 : tR[0], t_out = tR[nR - 1];
 
@@ -313,7 +316,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     int16_t* rEbuf = reinterpret_cast<int16_t*>(wbase + P.off_rE) + 1;
     int nDown = 0, nUp = 0;
     bool unchanged = false;
-    if constexpr (kAllCones) {
+    if (kMode != COOP_ORDINARY && all_cones) {
         // every cone, both roots, unsorted into the (still unused) merge buffers ...
         double* tmpT = reinterpret_cast<double*>(wbase + P.off_tEA);
         int32_t* tmpR = reinterpret_cast<int32_t*>(wbase + P.off_sEA) + 1;
@@ -351,7 +354,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
             }
         }
         nUp = n;
-    } else
+    } else if (kMode != COOP_ALLCONES)
     for (int k0 = 0; k0 < rec.e_count; k0 += 32) {
         const int k = k0 + lane;
         const int i = rec.e_first + k * rec.e_step;

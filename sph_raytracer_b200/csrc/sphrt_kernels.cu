@@ -486,12 +486,13 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 #endif
 constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
 constexpr int kCoopRecDoubles = 6;
+constexpr int64_t kCoopSplitRays = 4 << 20;    // from here on the all-cones rays get their own launch
 
 // phase 0 of the cooperative walker for one ray: load, set up, classify, plan; the float64 part of
 // the record goes to shared memory ([field][lane]), the integer part comes back in registers
 struct Phase0Result { int cls; int ri[6]; int64_t start_index; };
 
-template <bool kAllCones>
+template <int kMode>
 __device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, const KRays& kr, const CoopPlan& P,
                                                          int64_t i, int lane, double* recd,
                                                          CoopStartCache* cache, bool table_ok)
@@ -504,8 +505,8 @@ __device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, cons
     RayConsts c;
     ray_setup(c, x, d);
     CoopRecord rec;
-    r.cls = coop_plan_ray<kAllCones>(g, c, x, P, r.start_index, kr.cells, *cache, rec);
-    if (!table_ok && r.cls == COOP_RAY) r.cls = kAllCones ? COOP_LISTED : COOP_TRACKED;
+    r.cls = coop_plan_ray<kMode>(g, c, x, P, r.start_index, kr.cells, *cache, rec);
+    if (!table_ok && r.cls == COOP_RAY) r.cls = rec.e_mid == 0 ? COOP_LISTED : COOP_TRACKED;
     if (r.cls == COOP_RAY) {
         recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
         recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
@@ -518,23 +519,23 @@ __device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, cons
     return r;
 }
 
-template <bool kAllCones>
+template <int kMode>
 __device__ __noinline__ Phase0Result coop_phase0(GridView g, KRays kr, CoopPlan P, int64_t i, int lane,
                                                  double* recd, CoopStartCache* cache, bool table_ok)
 {
-    return coop_phase0_body<kAllCones>(g, kr, P, i, lane, recd, cache, table_ok);
+    return coop_phase0_body<kMode>(g, kr, P, i, lane, recd, cache, table_ok);
 }
 
-template <class Op, bool kAllCones>
+template <class Op, int kMode>
 __global__ void __launch_bounds__(kCoopMaxWarps * 32, 1)
 walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_mask,
                  uint32_t* listed_mask, uint32_t* tracked_mask, unsigned long long* tile_counter,
                  unsigned long long* stats)
 {
-    // kAllCones == false, in_mask == nullptr: every ray; rays that need the all-cones mode or pass B
-    // are flagged in listed_mask.  kAllCones == true: only the rays flagged in in_mask (by the run
-    // before, or by the per-thread walker on small grids), walked in all-cones mode; what is left
-    // over is flagged in listed_mask again (which may be in_mask itself: one warp owns a word).
+    // COOP_ORDINARY / COOP_BOTH, in_mask == nullptr: every ray; rays left for the all-cones run or
+    // pass B are flagged in listed_mask.  COOP_ALLCONES: only the rays flagged in in_mask (by the
+    // run before, or by the per-thread walker), walked in all-cones mode; what is left over is
+    // flagged in listed_mask again (which may be in_mask itself: one warp owns a word).
     extern __shared__ double sm_tables[];
     const GridView g = stage_tables(kg, sm_tables);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -562,9 +563,9 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
         if (i < kr.n && ((sel >> lane) & 1u)) {
 #ifdef SPHRT_PHASE0_NOINLINE
-            const Phase0Result r0 = coop_phase0<kAllCones>(g, kr, P, i, lane, recd, &start_cache, table_ok);
+            const Phase0Result r0 = coop_phase0<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
 #else
-            const Phase0Result r0 = coop_phase0_body<kAllCones>(g, kr, P, i, lane, recd, &start_cache, table_ok);
+            const Phase0Result r0 = coop_phase0_body<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
 #endif
             cls = r0.cls; start_index = r0.start_index;
             ri0 = r0.ri[0]; ri1 = r0.ri[1]; ri2 = r0.ri[2]; ri3 = r0.ri[3]; ri4 = r0.ri[4]; ri5 = r0.ri[5];
@@ -598,8 +599,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
             const double x[3] = {__ldg(xs), __ldg(xs + 1), __ldg(xs + 2)};
             CoopLists L;
             // a ray that fails a check goes back to the per-thread walker of its kind
-            uint32_t& m_back = kAllCones ? m_listed : m_tracked;
-            if (!coop_build<kAllCones>(g, P, wbase, rec, x, lane, L)) { m_back |= 1u << j; n_handed++; continue; }
+            uint32_t& m_back = rec.e_mid == 0 ? m_listed : m_tracked;
+            if (!coop_build<kMode>(g, P, wbase, rec, x, lane, L)) { m_back |= 1u << j; n_handed++; continue; }
             double* tEA; int32_t* sEA;
             const int nEA = coop_merge_ea(P, wbase, L, lane, tEA, sEA);
             if (nEA < 0) { m_back |= 1u << j; n_handed++; continue; }        // a list out of order
@@ -611,8 +612,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         }
         if (lane == 0) { listed_mask[tile] = m_listed; if (in_mask == nullptr) tracked_mask[tile] = m_tracked; }
         if (stats != nullptr && lane == 0) {
-            if (kAllCones) atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));    // left for pass B
-            else atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
+            if (kMode != COOP_ORDINARY) atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));    // left for pass B
+            if (kMode != COOP_ALLCONES) atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
         }
     }
     if (stats != nullptr && lane == 0) { atomicAdd(stats + 0, n_coop); atomicAdd(stats + 3, n_handed); }
@@ -837,17 +838,27 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
-            cudaFuncSetAttribute(walk_coop_kernel<Op, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            cudaFuncSetAttribute(walk_coop_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            walk_coop_kernel<Op, false><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
-            int rc = cuda_status();
-            if (rc != SPHRT_OK) return rc;
-            // the rays that need every cone evaluated and sorted (about 1 %), in place on their mask
-            walk_coop_kernel<Op, true><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, mask, mask, mask_tracked, counters + 3, stats);
-            rc = cuda_status();
-            if (rc != SPHRT_OK) return rc;
+            int rc;
+            if (rays->n_rays < kCoopSplitRays) {
+                // small problem: one launch for both kinds of ray
+                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_BOTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+                walk_coop_kernel<Op, COOP_BOTH><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                    *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
+                rc = cuda_status();
+                if (rc != SPHRT_OK) return rc;
+            } else {
+                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ORDINARY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ALLCONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+                walk_coop_kernel<Op, COOP_ORDINARY><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                    *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
+                rc = cuda_status();
+                if (rc != SPHRT_OK) return rc;
+                // the rays that need every cone evaluated and sorted (about 1 %), in place on their mask
+                walk_coop_kernel<Op, COOP_ALLCONES><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+                    *grid, kr, op, cl.P, mask, mask, mask_tracked, counters + 3, stats);
+                rc = cuda_status();
+                if (rc != SPHRT_OK) return rc;
+            }
             if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
             else {
             if (smem_a > 40 * 1024)   // (+ the static flag queue)
@@ -881,8 +892,8 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
         // all-cones mode first; pass B keeps what that cannot take (starts on a boundary ...)
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && !no_coop_listed()) {
-            cudaFuncSetAttribute(walk_coop_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            walk_coop_kernel<Op, true><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
+            cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ALLCONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+            walk_coop_kernel<Op, COOP_ALLCONES><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
                 *grid, kr, op, cl.P, mask, mask, nullptr, counters + 3, nullptr);
             rc = cuda_status();
             if (rc != SPHRT_OK) return rc;
