@@ -66,17 +66,10 @@ struct CoopRecord {           // what phase 1 needs to know about a ray (warp-un
     int se0, sa0;             // elevation / azimuth state at the entry point
 };
 
-// Phase 0 runs once per 32 rays; its big library routines are kept out of line so that the
-// kernel's hot loops stay close together in the instruction cache.
-#ifdef SPHRT_COOP_NOINLINE
-#define SPHRT_COLD __device__ __noinline__
-#else
-#define SPHRT_COLD __device__ __forceinline__
-#endif
-SPHRT_COLD double coop_atan2(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ double coop_atan2(double y, double x) { return atan2(y, x); }
 
 // geometric bins and reference states of a point, as start_voxel()
-SPHRT_COLD void coop_locate_point(const GridView& g, double p0, double p1, double p2, int bins[3],
+__device__ __forceinline__ void coop_locate_point(const GridView& g, double p0, double p1, double p2, int bins[3],
                                   int st[3], double sph[3])
 {
     const double xy = p0 * p0 + p1 * p1;
@@ -272,25 +265,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     const int m = g.nr - rec.imin + 1;
     const int nR = 2 * m;
     const double tang = 1e-17 * (1.0 + c.nx2);
-#ifdef SPHRT_COOP_UNROLL_R
-    // two shells per lane and step: two independent sqrt chains in flight
-    for (int k = lane; k < nR; k += 64) {
-        const int k2 = k + 32;
-        const bool out = k >= m, out2 = k2 >= m;
-        const int i = out ? rec.imin + (k - m) : g.nr - k;
-        int i2 = out2 ? rec.imin + (k2 - m) : g.nr - k2;
-        if (k2 >= nR) i2 = g.nr;
-        const double r = g.r_b()[i], rr = g.r_b()[i2];
-        const double r2 = r * r, rr2 = rr * rr;
-        const double arg = r2 - c.dperp2, arg2 = rr2 - c.dperp2;
-        const double t1c = sqrt(arg), t2c = sqrt(arg2);
-        const double tt = out ? c.tc + t1c : c.tc - t1c;
-        const double tt2 = out2 ? c.tc + t2c : c.tc - t2c;
-        if (!(arg >= tang + 1e-17 * r2) || !(arg2 >= tang + 1e-17 * rr2)) bad = true;
-        tR[k] = tt;
-        if (k2 < nR) tR[k2] = tt2;
-    }
-#else
     for (int k = lane; k < nR; k += 32) {
         const bool out = k >= m;
         const int i = out ? rec.imin + (k - m) : g.nr - k;
@@ -304,7 +278,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
         if (!(arg >= tang + 1e-17 * r2)) bad = true;
         tR[k] = tt;
     }
-#endif
     if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
     const bool all_cones = kMode == COOP_BOTH ? rec.e_mid == 0 : kMode == COOP_ALLCONES;
@@ -472,9 +445,6 @@ __device__ __forceinline__ int coop_corank(const double* X, int nX, const double
                                            int steps)
 {
     int lo = g - nY > 0 ? g - nY : 0, hi = g < nX ? g : nX;
-#ifdef SPHRT_CORANK_UNROLL
-#pragma unroll 4
-#endif
     for (int s = 0; s < steps; s++) {
         const int mid = (lo + hi) >> 1;
         const bool open = lo < hi;

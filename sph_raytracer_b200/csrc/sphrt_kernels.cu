@@ -99,12 +99,7 @@ __device__ __forceinline__ void load_ray(const KRays& kr, int64_t i, double x[3]
     const double* xs = kr.starts + 3 * (i / kr.rps);
     const double* ds = kr.dirs + 3 * (i / kr.rpd);
     x[0] = __ldg(xs); x[1] = __ldg(xs + 1); x[2] = __ldg(xs + 2);
-#ifdef SPHRT_STREAM_RAYS
-    // directions are read once per pass: stream them past the L2-resident volume
-    d[0] = __ldcs(ds); d[1] = __ldcs(ds + 1); d[2] = __ldcs(ds + 2);
-#else
     d[0] = __ldg(ds); d[1] = __ldg(ds + 1); d[2] = __ldg(ds + 2);
-#endif
 }
 
 // ---- per-ray operations ------------------------------------------------------------------
@@ -493,7 +488,7 @@ constexpr int64_t kCoopSplitRays = 4 << 20;    // from here on the all-cones ray
 struct Phase0Result { int cls; int ri[6]; int64_t start_index; };
 
 template <int kMode>
-__device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, const KRays& kr, const CoopPlan& P,
+__device__ __forceinline__ Phase0Result coop_phase0(const GridView& g, const KRays& kr, const CoopPlan& P,
                                                          int64_t i, int lane, double* recd,
                                                          CoopStartCache* cache, bool table_ok)
 {
@@ -517,13 +512,6 @@ __device__ __forceinline__ Phase0Result coop_phase0_body(const GridView& g, cons
         r.ri[5] = (rec.se0 & 0xffff) | (rec.sa0 << 16);
     }
     return r;
-}
-
-template <int kMode>
-__device__ __noinline__ Phase0Result coop_phase0(GridView g, KRays kr, CoopPlan P, int64_t i, int lane,
-                                                 double* recd, CoopStartCache* cache, bool table_ok)
-{
-    return coop_phase0_body<kMode>(g, kr, P, i, lane, recd, cache, table_ok);
 }
 
 template <class Op, int kMode>
@@ -562,11 +550,7 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         const uint32_t sel = in_mask != nullptr ? __ldg(in_mask + tile) : 0xffffffffu;
         if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
         if (i < kr.n && ((sel >> lane) & 1u)) {
-#ifdef SPHRT_PHASE0_NOINLINE
             const Phase0Result r0 = coop_phase0<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
-#else
-            const Phase0Result r0 = coop_phase0_body<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
-#endif
             cls = r0.cls; start_index = r0.start_index;
             ri0 = r0.ri[0]; ri1 = r0.ri[1]; ri2 = r0.ri[2]; ri3 = r0.ri[3]; ri4 = r0.ri[4]; ri5 = r0.ri[5];
         }
@@ -812,7 +796,66 @@ int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const u
     return cuda_status();
 }
 
-// scratch layout: [listed mask][tracked mask][global cone lists, if any]
+// Everything a pass needs to know about the launch: rays, scratch carved into its parts.
+struct PassContext {
+    const sphrt_grid* grid;
+    KRays kr;
+    cudaStream_t st;
+    size_t smem_tables;                  // bytes of boundary tables in shared memory
+    uint32_t* mask_listed;               // rays for the sorted-list walkers (all-cones run, pass B)
+    uint32_t* mask_tracked;              // rays the cooperative walker hands to the per-thread walker
+    unsigned long long* counters;        // [0] cooperative tiles  [1] masked per-thread pass
+                                         // [2] pass B  [3] cooperative all-cones tiles
+    void* lists;                         // global cone lists of pass B (very large grids only)
+    int64_t n_words;
+};
+
+template <class Op, int kMode>
+int launch_coop(const PassContext& cx, const CoopLaunch& cl, const Op& op, const uint32_t* in_mask,
+                unsigned long long* tile_counter, unsigned long long* stats)
+{
+    cudaFuncSetAttribute(walk_coop_kernel<Op, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
+    walk_coop_kernel<Op, kMode><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, cx.st>>>(
+        *cx.grid, cx.kr, op, cl.P, in_mask, cx.mask_listed, cx.mask_tracked, tile_counter, stats);
+    return cuda_status();
+}
+
+template <class Op>
+int launch_tracked_masked(const PassContext& cx, const Op& op)
+{
+    const size_t smem = cx.smem_tables + kQueueBytes;
+    if (smem > 40 * 1024)   // (+ the static flag queue)
+        cudaFuncSetAttribute(walk_tracked_masked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int64_t blocks = (int64_t)num_sms() * SPHRT_TRACKED_MIN_BLOCKS;
+    const int64_t want = (cx.n_words + 32 * (kBlock / 32) - 1) / (32 * (kBlock / 32));
+    if (blocks > want) blocks = want;
+    if (blocks < 1) blocks = 1;
+    walk_tracked_masked_kernel<Op><<<(unsigned)blocks, kBlock, smem, cx.st>>>(
+        *cx.grid, cx.kr, op, (int)(cx.smem_tables / sizeof(double)), cx.mask_tracked, cx.n_words,
+        cx.counters + 1);
+    return cuda_status();
+}
+
+template <class Op>
+int launch_tracked_dense(const PassContext& cx, const Op& op)
+{
+    const size_t smem = cx.smem_tables + kQueueBytes;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t blocks = (cx.kr.n + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffLL) return SPHRT_ETOOBIG;
+    walk_tracked_kernel<Op><<<(unsigned)blocks, kBlock, smem, cx.st>>>(
+        *cx.grid, cx.kr, op, (int)(cx.smem_tables / sizeof(double)), cx.mask_listed);
+    return cuda_status();
+}
+
+// Walk every ray with `op`.  Scratch layout: [listed mask][tracked mask][counters][global cone lists].
+//
+//   cooperative path : cooperative walker (ordinary rays, then the all-cones rays; one launch for
+//                      both below kCoopSplitRays) -> per-thread walker on what it handed over
+//                      -> pass B on what is left of the sorted-list rays
+//   per-thread path  : per-thread walker -> cooperative all-cones run on its sorted-list rays
+//                      (ops that can run cooperatively) -> pass B on what is left
 template <class Op>
 int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
                   void* scratch, int64_t scratch_bytes, void* stream, bool force_coop = false,
@@ -820,86 +863,61 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
 {
     if (rays->n_rays == 0) return SPHRT_OK;
     if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
-    cudaStream_t st = (cudaStream_t)stream;
-    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
-                   rays->start_cells};
-    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
-    const size_t smem_a = smem + kQueueBytes;
+    PassContext cx;
+    cx.grid = grid;
+    cx.kr = KRays{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
+                  rays->start_cells};
+    cx.st = (cudaStream_t)stream;
+    cx.smem_tables = (size_t)table_doubles(*grid) * sizeof(double);
+    cx.mask_listed = (uint32_t*)scratch;
+    cx.mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
+    cx.counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
+    cx.lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
+    cx.n_words = (rays->n_rays + 31) / 32;
+    cudaMemsetAsync(cx.counters, 0, 4 * sizeof(unsigned long long), cx.st);
     const ListPlan lp = plan_lists(*grid, rays->n_rays);
-    uint32_t* mask = (uint32_t*)scratch;
-    uint32_t* mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
-    void* lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
-    const int64_t n_words = (rays->n_rays + 31) / 32;
-    // work hand-out counters: [0] cooperative tiles, [1] masked per-thread pass, [2] listed pass,
-    // [3] cooperative all-cones tiles
-    unsigned long long* counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
-    cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st);
+    int rc;
 
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
-            int rc;
             if (rays->n_rays < kCoopSplitRays) {
-                // small problem: one launch for both kinds of ray
-                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_BOTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-                walk_coop_kernel<Op, COOP_BOTH><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                    *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
-                rc = cuda_status();
-                if (rc != SPHRT_OK) return rc;
+                rc = launch_coop<Op, COOP_BOTH>(cx, cl, op, nullptr, cx.counters, stats);
             } else {
-                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ORDINARY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-                cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ALLCONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-                walk_coop_kernel<Op, COOP_ORDINARY><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                    *grid, kr, op, cl.P, nullptr, mask, mask_tracked, counters, stats);
-                rc = cuda_status();
-                if (rc != SPHRT_OK) return rc;
+                rc = launch_coop<Op, COOP_ORDINARY>(cx, cl, op, nullptr, cx.counters, stats);
                 // the rays that need every cone evaluated and sorted (about 1 %), in place on their mask
-                walk_coop_kernel<Op, COOP_ALLCONES><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                    *grid, kr, op, cl.P, mask, mask, mask_tracked, counters + 3, stats);
-                rc = cuda_status();
+                if (rc == SPHRT_OK)
+                    rc = launch_coop<Op, COOP_ALLCONES>(cx, cl, op, cx.mask_listed, cx.counters + 3, stats);
+            }
+            if (rc != SPHRT_OK) return rc;
+            if constexpr (Op::kEvents) {
+                return SPHRT_OK;               // raw event export: cooperative walker only
+            } else {
+                rc = launch_tracked_masked(cx, op);
+                if (rc != SPHRT_OK) return rc;
+                return launch_listed(grid, cx.kr, op, cx.mask_listed, cx.lists, cx.smem_tables, lp,
+                                     cx.counters + 2, cx.st);
+            }
+        }
+    }
+    if constexpr (Op::kEvents) {
+        return SPHRT_ETOOBIG;                  // the event export has no per-thread form
+    } else {
+        rc = launch_tracked_dense(cx, op);
+        if (rc != SPHRT_OK) return rc;
+        if constexpr (Op::kCoop) {
+            // The sorted-list rays are a few per cent of the rays but, walked by one thread each,
+            // more than half of a step on the 50^3 grids: walk them cooperatively in all-cones mode
+            // first; pass B keeps what that cannot take (starts inside the grid, rays through the
+            // Z axis).  SPHRT_COOP_LISTED=0 leaves them all to pass B (tests).
+            const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
+            if (cl.ok && !no_coop_listed()) {
+                rc = launch_coop<Op, COOP_ALLCONES>(cx, cl, op, cx.mask_listed, cx.counters + 3, nullptr);
                 if (rc != SPHRT_OK) return rc;
             }
-            if constexpr (Op::kEvents) return rc;  // raw event export: cooperative walker only
-            else {
-            if (smem_a > 40 * 1024)   // (+ the static flag queue)
-                cudaFuncSetAttribute(walk_tracked_masked_kernel<Op>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-            int64_t blocks_m = (int64_t)num_sms() * SPHRT_TRACKED_MIN_BLOCKS;
-            const int64_t want = (n_words + 32 * (kBlock / 32) - 1) / (32 * (kBlock / 32));
-            if (blocks_m > want) blocks_m = want;
-            if (blocks_m < 1) blocks_m = 1;
-            walk_tracked_masked_kernel<Op><<<(unsigned)blocks_m, kBlock, smem_a, st>>>(
-                *grid, kr, op, (int)(smem / sizeof(double)), mask_tracked, n_words, counters + 1);
-            rc = cuda_status();
-            if (rc != SPHRT_OK) return rc;
-            return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
-            }
         }
-    }
-    if constexpr (Op::kEvents) return SPHRT_ETOOBIG;
-    else {
-    if (smem_a > 48 * 1024)
-        cudaFuncSetAttribute(walk_tracked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-    const int64_t blocks_a = (rays->n_rays + kBlock - 1) / kBlock;
-    if (blocks_a > 0x7fffffffLL) return SPHRT_ETOOBIG;
-    walk_tracked_kernel<Op><<<(unsigned)blocks_a, kBlock, smem_a, st>>>(*grid, kr, op,
-                                                                       (int)(smem / sizeof(double)), mask);
-    int rc = cuda_status();
-    if (rc != SPHRT_OK) return rc;
-    if constexpr (Op::kCoop) {
-        // the rays that need the sorted cone list are a few per cent of the rays but (walked by one
-        // thread each) more than half of a step on the 50^3 grids: walk them cooperatively in
-        // all-cones mode first; pass B keeps what that cannot take (starts on a boundary ...)
-        const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
-        if (cl.ok && !no_coop_listed()) {
-            cudaFuncSetAttribute(walk_coop_kernel<Op, COOP_ALLCONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl.smem);
-            walk_coop_kernel<Op, COOP_ALLCONES><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, st>>>(
-                *grid, kr, op, cl.P, mask, mask, nullptr, counters + 3, nullptr);
-            rc = cuda_status();
-            if (rc != SPHRT_OK) return rc;
-        }
-    }
-    return launch_listed(grid, kr, op, mask, lists, smem, lp, counters + 2, st);
+        return launch_listed(grid, cx.kr, op, cx.mask_listed, cx.lists, cx.smem_tables, lp,
+                             cx.counters + 2, cx.st);
     }
 }
 
