@@ -170,3 +170,42 @@ def test_sharded_operator_gloo_world2():
         assert np.allclose(y, full[lo:hi])
         assert np.allclose(gx, grad)       # gradient is global (all-reduced) on every rank
         assert np.allclose(ty, grad)
+
+
+def test_start_cells_match_find_starts():
+    """The host-side binning of start points (what sphrt_rays.start_cells carries) is the
+    reference's find_starts: known answers of the reference's own tests, the C oracle on random
+    points, and the on-boundary flag."""
+    import numpy as np
+    from oracle import oracle as O
+    z = np.load(os.path.join(ROOT, "tests", "golden", "known_answers.npz"))
+    for row in z["find_starts"]:
+        shape, x, want = row[:3].astype(int), row[3:6], row[6:9].astype(int)
+        grid = S.SphericalGrid(shape=tuple(shape))
+        cells = R._start_cells(grid.r_b.double(), grid.e_b.double(), grid.a_b.double(),
+                               torch.tensor(x, dtype=torch.float64)[None])
+        assert cells[0, 3:6].tolist() == want.tolist()
+    grid = S.SphericalGrid((7, 9, 11), size_r=(0.5, 3), size_e=(0.3, 2.9), size_a=(-2.5, 2.9))
+    pts = torch.randn(5000, 3, generator=torch.Generator().manual_seed(0), dtype=torch.float64) * 2
+    cells = R._start_cells(grid.r_b.double(), grid.e_b.double(), grid.a_b.double(), pts).numpy()
+    og = O.OracleGrid(grid)
+    want = np.asarray(O.find_starts(og, pts.numpy())).reshape(3, -1)
+    assert (cells[:, 3:6].T == want).all()
+    assert not cells[:, 6].any()                       # random points are on no boundary
+    # geometric bins keep the "beyond the last boundary" bin that the states map to -1
+    assert ((cells[:, 0:3] == cells[:, 3:6]) | (cells[:, 3:6] == -1)).all()
+    full = S.SphericalGrid((4, 4, 8))
+    on = R._start_cells(full.r_b.double(), full.e_b.double(), full.a_b.double(),
+                        torch.tensor([[5.0, 0.0, 0.0], [3.0, 3.0, 1.0], [1.0, 0.2, 0.3]], dtype=torch.float64))
+    assert on[:, 6].tolist() == [1, 1, 0]              # (5,0,0): equator cone and plane a = 0; (3,3,1): a = pi/4
+
+
+def test_canonical_from_events():
+    import numpy as np
+    from helpers import canonical_from_events
+    vox = np.array([[[1, 1, 1], [1, 1, 1], [1, 2, 1], [-1, 2, 1], [0, 0, 0]]], dtype=np.int32)
+    lens = np.array([[0.5, 0.25, 0.0, 0.0, 9.0]])
+    c, v, l = canonical_from_events(vox, lens, np.array([4]), 4)
+    assert c.tolist() == [1] and v[0, 0].tolist() == [1, 1, 1] and l[0, 0] == 0.75
+    c, v, l = canonical_from_events(vox, lens, np.array([-1]), 4)
+    assert c.tolist() == [-1]
