@@ -281,6 +281,47 @@ def run_gpu(args):
     elapsed_ms, e2e_ms, t_fwd, t_adj, peak_bytes = stats.tolist()
     tot_seg, tot_rays = sums.tolist()
 
+    # Extra, not the headline: the same step with the STORED operator (Operator(store_segments=True):
+    # the reference's own design, segments traced once and kept as an 8-byte-per-segment list),
+    # where that list fits next to everything else -- at config 5 from four GPUs on.
+    stored = None
+    if os.environ.get("SPHRT_BENCH_STORED", "1") != "0" and not dynamic:
+        def agree(flag):                 # every rank takes the same branch: minimum over the ranks
+            t = torch.tensor([1.0 if flag else 0.0], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return t.item() > 0
+        out = g = None
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0]
+        if agree(8.0 * n_seg + 8.0 * n_rays < 0.6 * free):
+            t0 = time.perf_counter()
+            try:
+                op._store(torch.float32)
+                torch.cuda.synchronize(dev)
+                built = True
+            except Exception:            # e.g. out of memory on one rank: all ranks skip together
+                built = False
+            t_store = time.perf_counter() - t0
+            if agree(built):
+                for _ in range(2):
+                    step_device()
+                barrier()
+                sev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                sev[0].record()
+                for _ in range(args.steps):
+                    step_device()
+                sev[1].record()
+                barrier()
+                st = torch.tensor([sev[0].elapsed_time(sev[1]) / args.steps, t_store * 1e3, float(op.stored_bytes)],
+                                  dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+                stored = {"value": 2 * tot_seg / (st[0].item() / 1e3), "unit": "ray-segments/s",
+                          "ms_per_step": st[0].item(), "store_ms": st[1].item(),
+                          "stored_gb_per_gpu": st[2].item() / 1e9,
+                          "note": "same step through the stored operator; not the headline value"}
+
     if rank == 0:
         ms = elapsed_ms / args.steps
         e2e_step = e2e_ms / args.steps
@@ -331,6 +372,8 @@ def run_gpu(args):
             "peak_memory_gb": peak_bytes / 1e9,
             "operator_build_s": t_build,
         }
+        if stored is not None:
+            line["stored_operator"] = stored
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(args.workload)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
