@@ -1,7 +1,7 @@
 """Differential fuzzing against the CPU oracle: random grids, rays of several kinds (aimed from
 outside, starting inside, starting exactly on grid planes / cones / axes, axis-parallel), every ray
 compared through BOTH GPU walkers' integrals (float64) with the oracle's, plus canonical sequences
-of the per-thread walker.  Usage: fuzz.py [n_grids] [rays_per_kind] [seed]"""
+of the per-thread walker.  Usage: fuzz.py [n_grids] [rays_per_kind] [seed] [max voxels per axis]"""
 import os, sys, math, numpy as np, torch
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
@@ -9,12 +9,12 @@ import sph_raytracer_b200 as S
 from oracle import oracle as O
 
 
-def run(n_grids=12, n=3000, seed=0, verbose=True):
+def run(n_grids=12, n=3000, seed=0, max_axis=70, verbose=True):
     rng = np.random.default_rng(seed)
     g = torch.Generator().manual_seed(seed)
     tot_bad = 0
     for k in range(n_grids):
-        shape = tuple(int(v) for v in rng.integers(3, 70, 3))
+        shape = tuple(int(v) for v in rng.integers(3, max_axis, 3))
         r0 = float(rng.choice([0.0, 0.3, 1.0])); r1 = r0 + float(rng.uniform(0.5, 4))
         kw = dict(size_r=(r0, r1))
         if rng.random() < 0.3 and r0 > 0: kw["spacing"] = "log"
