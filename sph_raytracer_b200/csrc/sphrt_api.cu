@@ -1,0 +1,126 @@
+// sphrt_api.cu -- the rest of the C ABI of libsphrt.so: queries, counting / trace / store /
+// event exports, stored-operator passes, find_starts.
+#include "sphrt_kernels.cuh"
+
+int sphrt_g_last_cuda_error = 0;
+
+// ---- C ABI --------------------------------------------------------------------------------------
+
+extern "C" {
+
+int sphrt_version(void) { return SPHRT_VERSION; }
+
+int sphrt_last_cuda_error(void) { return sphrt_g_last_cuda_error; }
+
+const char* sphrt_error_string(int code)
+{
+    switch (code) {
+    case SPHRT_OK: return "ok";
+    case SPHRT_EINVAL: return "invalid argument";
+    case SPHRT_ETOOBIG: return "grid axis or ray count too large";
+    case SPHRT_ESCRATCH: return "scratch buffer missing or smaller than sphrt_scratch_bytes()";
+    case SPHRT_ECUDA: return "CUDA launch failed";
+    default: return "unknown error";
+    }
+}
+
+int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
+{
+    if (grid == nullptr || grid->ne < 1 || n_rays < 0) return 0;
+    int64_t bytes = 2 * mask_bytes(n_rays) + 256;     // + tile counter of the cooperative walker
+    const ListPlan lp = plan_lists(*grid, n_rays);
+    if (lp.global_lists)
+        bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
+    return bytes;
+}
+
+
+
+int sphrt_count_segments(const sphrt_grid* grid, const sphrt_rays* rays, int32_t* count,
+                         unsigned long long* total, void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays > 0 && !count) return SPHRT_EINVAL;
+    const CountOp op{count, total};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_trace_segments(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_seg,
+                         int32_t* vox, double* seg_len, int32_t* count, void* scratch,
+                         int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (max_seg < 1) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!vox || !seg_len || !count)) return SPHRT_EINVAL;
+    const TraceOp op{vox, seg_len, count, max_seg};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_store_segments(const sphrt_grid* grid, const sphrt_rays* rays, const int64_t* offsets,
+                         int32_t* vox, void* seg_len, int len_dtype, void* scratch,
+                         int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays > 0 && (!offsets || !vox || !seg_len)) return SPHRT_EINVAL;
+    if (len_dtype == SPHRT_F32) {
+        const StoreOp<float> op{offsets, vox, (float*)seg_len, grid->ne, grid->na};
+        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+    }
+    if (len_dtype == SPHRT_F64) {
+        const StoreOp<double> op{offsets, vox, (double*)seg_len, grid->ne, grid->na};
+        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+    }
+    return SPHRT_EINVAL;
+}
+
+int sphrt_forward_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
+                         int64_t n_rays, const void* density, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void* out, void* stream)
+{
+    return dispatch_stored<false>(offsets, vox, seg_len, len_dtype, n_rays, density, dtype, out, n_vol,
+                                  rays_per_vol, nvox, stream);
+}
+
+int sphrt_adjoint_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
+                         int64_t n_rays, const void* y, int dtype, int64_t n_vol,
+                         int64_t rays_per_vol, int64_t nvox, void* grad, void* stream)
+{
+    return dispatch_stored<true>(offsets, vox, seg_len, len_dtype, n_rays, y, dtype, grad, n_vol,
+                                 rays_per_vol, nvox, stream);
+}
+
+int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_ev,
+                       int32_t* vox, double* ev_len, int32_t* count, unsigned long long* stats,
+                       void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (max_ev < 1) return SPHRT_EINVAL;
+    if (rays->n_rays > 0 && (!vox || !ev_len || !count)) return SPHRT_EINVAL;
+    const EventTraceOp op{vox, ev_len, count, max_ev};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream, true, stats);
+}
+
+int sphrt_walker_kind(const sphrt_grid* grid, int64_t n_rays)
+{
+    if (check_grid(grid) != SPHRT_OK) return SPHRT_EINVAL;
+    return (plan_coop(*grid, n_rays).ok && want_coop(*grid)) ? 1 : 0;
+}
+
+int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!xs || !out))) return SPHRT_EINVAL;
+    if (n == 0) return SPHRT_OK;
+    const int64_t blocks = (n + kBlock - 1) / kBlock;
+    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    find_starts_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(*grid, n, xs, out);
+    return cuda_status();
+}
+
+}  // extern "C"

@@ -1,4 +1,7 @@
-// sphrt_kernels.cu -- sm_100a kernels and the C ABI of libsphrt.so (include/sphrt.h).
+#pragma once
+// sphrt_kernels.cuh -- sm_100a kernels and their host launchers (C ABI: sphrt_forward.cu,
+// sphrt_adjoint.cu, sphrt_api.cu; include/sphrt.h).  Three translation units include this header
+// so that nvcc compiles the forward, adjoint and export kernels in parallel.
 //
 // One thread walks one ray with the register-resident crossing merge of
 // sphrt_walker.cuh; nothing per ray-slot is ever materialised (the reference stores
@@ -44,7 +47,10 @@ constexpr int kMaxSmemBytes = 96 * 1024;   // boundary tables must fit in shared
 constexpr int kQueue = SPHRT_QUEUE;    // pass A: events buffered per stream and thread
 constexpr int kQueueBytes = 3 * kQueue * kBlock * (int)(sizeof(double) + sizeof(int));
 
-static int g_last_cuda_error = 0;
+// one slot for the whole library (defined in sphrt_api.cu): the last cudaError_t a launch returned
+}  // namespace
+extern int sphrt_g_last_cuda_error;
+namespace {
 
 struct KRays {
     int64_t n;
@@ -773,7 +779,7 @@ int check_rays(const sphrt_rays* r)
 int cuda_status()
 {
     const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return SPHRT_ECUDA; }
+    if (e != cudaSuccess) { sphrt_g_last_cuda_error = (int)e; return SPHRT_ECUDA; }
     return SPHRT_OK;
 }
 
@@ -934,11 +940,20 @@ int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in
         OpT<T, 1> op{in, out, m, 0};
         return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
     }
-    // channels share the geometry: walk once per group of 4 volumes
-    for (int64_t ch0 = 0; ch0 < n_vol; ch0 += 4) {
-        OpT<T, 4> op{in, out, m, (int)ch0};
-        const int rc = launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
-        if (rc != SPHRT_OK) return rc;
+    // channels share the geometry: float32 volumes are walked four at a time, float64 volumes
+    // (rare; their 4-wide kernels would be a third of this library's compile time) one by one
+    if constexpr (sizeof(T) == 4) {
+        for (int64_t ch0 = 0; ch0 < n_vol; ch0 += 4) {
+            OpT<T, 4> op{in, out, m, (int)ch0};
+            const int rc = launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+            if (rc != SPHRT_OK) return rc;
+        }
+    } else {
+        for (int64_t ch0 = 0; ch0 < n_vol; ch0++) {
+            OpT<T, 1> op{in, out, m, (int)ch0};
+            const int rc = launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+            if (rc != SPHRT_OK) return rc;
+        }
     }
     return SPHRT_OK;
 }
@@ -1016,155 +1031,3 @@ int dispatch_stored(const int64_t* offsets, const int32_t* vox, const void* seg_
 
 }  // namespace
 
-// ---- C ABI --------------------------------------------------------------------------------------
-
-extern "C" {
-
-int sphrt_version(void) { return SPHRT_VERSION; }
-
-int sphrt_last_cuda_error(void) { return g_last_cuda_error; }
-
-const char* sphrt_error_string(int code)
-{
-    switch (code) {
-    case SPHRT_OK: return "ok";
-    case SPHRT_EINVAL: return "invalid argument";
-    case SPHRT_ETOOBIG: return "grid axis or ray count too large";
-    case SPHRT_ESCRATCH: return "scratch buffer missing or smaller than sphrt_scratch_bytes()";
-    case SPHRT_ECUDA: return "CUDA launch failed";
-    default: return "unknown error";
-    }
-}
-
-int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
-{
-    if (grid == nullptr || grid->ne < 1 || n_rays < 0) return 0;
-    int64_t bytes = 2 * mask_bytes(n_rays) + 256;     // + tile counter of the cooperative walker
-    const ListPlan lp = plan_lists(*grid, n_rays);
-    if (lp.global_lists)
-        bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
-    return bytes;
-}
-
-int sphrt_forward(const sphrt_grid* grid, const sphrt_rays* rays, const void* density, int dtype,
-                  int64_t n_vol, int64_t rays_per_vol, void* out, void* scratch,
-                  int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (n_vol < 1 || rays_per_vol < 0) return SPHRT_EINVAL;
-    if (rays->n_rays > 0 && (!density || !out)) return SPHRT_EINVAL;
-    if (dtype == SPHRT_F32)
-        return launch_volume_op<ForwardOp, float>(grid, rays, (const float*)density, (float*)out, n_vol,
-                                                  rays_per_vol, true, scratch, scratch_bytes, stream);
-    if (dtype == SPHRT_F64)
-        return launch_volume_op<ForwardOp, double>(grid, rays, (const double*)density, (double*)out, n_vol,
-                                                   rays_per_vol, true, scratch, scratch_bytes, stream);
-    return SPHRT_EINVAL;
-}
-
-int sphrt_adjoint(const sphrt_grid* grid, const sphrt_rays* rays, const void* y, int dtype,
-                  int64_t n_vol, int64_t rays_per_vol, void* grad, void* scratch,
-                  int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (n_vol < 1 || rays_per_vol < 0) return SPHRT_EINVAL;
-    if (rays->n_rays > 0 && (!y || !grad)) return SPHRT_EINVAL;
-    if (dtype == SPHRT_F32)
-        return launch_volume_op<AdjointOp, float>(grid, rays, (const float*)y, (float*)grad, n_vol,
-                                                  rays_per_vol, false, scratch, scratch_bytes, stream);
-    if (dtype == SPHRT_F64)
-        return launch_volume_op<AdjointOp, double>(grid, rays, (const double*)y, (double*)grad, n_vol,
-                                                   rays_per_vol, false, scratch, scratch_bytes, stream);
-    return SPHRT_EINVAL;
-}
-
-int sphrt_count_segments(const sphrt_grid* grid, const sphrt_rays* rays, int32_t* count,
-                         unsigned long long* total, void* scratch, int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (rays->n_rays > 0 && !count) return SPHRT_EINVAL;
-    const CountOp op{count, total};
-    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
-}
-
-int sphrt_trace_segments(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_seg,
-                         int32_t* vox, double* seg_len, int32_t* count, void* scratch,
-                         int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (max_seg < 1) return SPHRT_EINVAL;
-    if (rays->n_rays > 0 && (!vox || !seg_len || !count)) return SPHRT_EINVAL;
-    const TraceOp op{vox, seg_len, count, max_seg};
-    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
-}
-
-int sphrt_store_segments(const sphrt_grid* grid, const sphrt_rays* rays, const int64_t* offsets,
-                         int32_t* vox, void* seg_len, int len_dtype, void* scratch,
-                         int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (rays->n_rays > 0 && (!offsets || !vox || !seg_len)) return SPHRT_EINVAL;
-    if (len_dtype == SPHRT_F32) {
-        const StoreOp<float> op{offsets, vox, (float*)seg_len, grid->ne, grid->na};
-        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
-    }
-    if (len_dtype == SPHRT_F64) {
-        const StoreOp<double> op{offsets, vox, (double*)seg_len, grid->ne, grid->na};
-        return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
-    }
-    return SPHRT_EINVAL;
-}
-
-int sphrt_forward_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
-                         int64_t n_rays, const void* density, int dtype, int64_t n_vol,
-                         int64_t rays_per_vol, int64_t nvox, void* out, void* stream)
-{
-    return dispatch_stored<false>(offsets, vox, seg_len, len_dtype, n_rays, density, dtype, out, n_vol,
-                                  rays_per_vol, nvox, stream);
-}
-
-int sphrt_adjoint_stored(const int64_t* offsets, const int32_t* vox, const void* seg_len, int len_dtype,
-                         int64_t n_rays, const void* y, int dtype, int64_t n_vol,
-                         int64_t rays_per_vol, int64_t nvox, void* grad, void* stream)
-{
-    return dispatch_stored<true>(offsets, vox, seg_len, len_dtype, n_rays, y, dtype, grad, n_vol,
-                                 rays_per_vol, nvox, stream);
-}
-
-int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_ev,
-                       int32_t* vox, double* ev_len, int32_t* count, unsigned long long* stats,
-                       void* scratch, int64_t scratch_bytes, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    rc = check_rays(rays); if (rc) return rc;
-    if (max_ev < 1) return SPHRT_EINVAL;
-    if (rays->n_rays > 0 && (!vox || !ev_len || !count)) return SPHRT_EINVAL;
-    const EventTraceOp op{vox, ev_len, count, max_ev};
-    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream, true, stats);
-}
-
-int sphrt_walker_kind(const sphrt_grid* grid, int64_t n_rays)
-{
-    if (check_grid(grid) != SPHRT_OK) return SPHRT_EINVAL;
-    return (plan_coop(*grid, n_rays).ok && want_coop(*grid)) ? 1 : 0;
-}
-
-int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)
-{
-    int rc = check_grid(grid); if (rc) return rc;
-    if (n < 0 || (n > 0 && (!xs || !out))) return SPHRT_EINVAL;
-    if (n == 0) return SPHRT_OK;
-    const int64_t blocks = (n + kBlock - 1) / kBlock;
-    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    find_starts_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(*grid, n, xs, out);
-    return cuda_status();
-}
-
-}  // extern "C"

@@ -7,7 +7,7 @@ attributes, ``repr``; reference ``raytracer.py:647-755``) and ``find_starts``
 crossing as ``regs (3,*rays,K) int64`` / ``lens (*rays,K) float64`` (``trace_indices``,
 ``:48-230``) and then gathers (``:710-713``), this operator keeps only the rays on the
 GPU and regenerates the crossings inside fused CUDA kernels on every call
-(``csrc/sphrt_kernels.cu`` through the C ABI of ``include/sphrt.h``).
+(``csrc/sphrt_kernels.cuh`` through the C ABI of ``include/sphrt.h``).
 
 There is no CPU implementation here.  Host tensors are accepted (they are copied to the
 GPU and the result is copied back, so reference-style CPU callers keep working), but
