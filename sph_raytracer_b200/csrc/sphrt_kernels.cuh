@@ -140,14 +140,10 @@ struct ForwardOp {
         __device__ __forceinline__ void segment_at(bool ok, int r, int e, int a, double len)
         {
             if constexpr (NCH == 1) {
-#ifdef SPHRT_FWD_DIRECT
-                if (ok) acc[0] = fma_rn((double)__ldg(vol + (r * ne + e) * na + a), len, acc[0]);
-#else
                 acc[0] = fma_rn((double)rval[SLOT], rlen[SLOT], acc[0]);
                 const int idx = ok ? (r * ne + e) * na + a : 0;
                 rval[SLOT] = __ldg(vol + idx);
                 rlen[SLOT] = ok ? len : 0.0;
-#endif
             } else {
                 if (ok) segment(r, e, a, len);
             }
