@@ -372,6 +372,19 @@ def run_gpu(args):
             "peak_memory_gb": peak_bytes / 1e9,
             "operator_build_s": t_build,
         }
+        # the bounds that are actually near: one L2 gather / one L2 fp32 reduction per
+        # segment against the measured peaks of tools/microbench/peaks.cu (profiles/)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1c_secondary_peaks.json")) as f:
+                pk = json.load(f)
+            line["l2_rooflines"] = {
+                "forward_gathers_per_s": seg_r / (t_fwd / 1e3), "gather_peak_per_s": pk["l2_random_gather_per_s"],
+                "forward_frac": seg_r / (t_fwd / 1e3) / pk["l2_random_gather_per_s"],
+                "adjoint_reds_per_s": seg_r / (t_adj / 1e3), "red_peak_per_s": pk["l2_random_red_f32_per_s"],
+                "adjoint_frac": seg_r / (t_adj / 1e3) / pk["l2_random_red_f32_per_s"],
+                "peak_source": "tools/microbench/peaks.cu on this GPU model (profiles/r1c_secondary_peaks.json)"}
+        except Exception:
+            pass
         if stored is not None:
             line["stored_operator"] = stored
         if world == 1 and not args.no_cpu_baseline:
