@@ -504,7 +504,7 @@ __device__ __forceinline__ int coop_merge_ea(const CoopPlan& P, char* wbase, con
 #ifndef SPHRT_COOP_DEPTH
 #define SPHRT_COOP_DEPTH 1
 #endif
-constexpr int kCoopDepth = SPHRT_COOP_DEPTH;      // 1, 2 or 4
+constexpr int kCoopDepth = SPHRT_COOP_DEPTH;      // unroll of gathering sinks (Sink::kDepth): 1, 2 or 4
 
 template <bool kEvents, class Sink>
 __device__ __forceinline__ void coop_segments(const CoopLists& L, const double* tEA, const int32_t* sEA,
@@ -543,13 +543,14 @@ __device__ __forceinline__ void coop_segments(const CoopLists& L, const double* 
         t = tn; g++;                                                                              \
     }
     const int g_end = g0 + c;
-    while (g + kCoopDepth <= g_end) {
+    constexpr int kDepth = Sink::kDepth;           // 1 for sinks without loads to hide
+    while (g + kDepth <= g_end) {
         SPHRT_COOP_STEP(0)
-        if constexpr (kCoopDepth > 1) SPHRT_COOP_STEP(1)
-        if constexpr (kCoopDepth > 2) { SPHRT_COOP_STEP(2) SPHRT_COOP_STEP(3) }
+        if constexpr (kDepth > 1) SPHRT_COOP_STEP(1)
+        if constexpr (kDepth > 2) { SPHRT_COOP_STEP(2) SPHRT_COOP_STEP(3) }
     }
-    if constexpr (kCoopDepth > 1) { if (g < g_end) SPHRT_COOP_STEP(0) }
-    if constexpr (kCoopDepth > 2) { if (g < g_end) SPHRT_COOP_STEP(1) if (g < g_end) SPHRT_COOP_STEP(2) }
+    if constexpr (kDepth > 1) { if (g < g_end) SPHRT_COOP_STEP(0) }
+    if constexpr (kDepth > 2) { if (g < g_end) SPHRT_COOP_STEP(1) if (g < g_end) SPHRT_COOP_STEP(2) }
 #undef SPHRT_COOP_STEP
 }
 

@@ -135,6 +135,7 @@ struct ForwardOp {
         T pval[NCH];
         // cooperative walker: kCoopDepth gathers in flight per lane (slot k is consumed when the
         // k-th next segment arrives); one channel only, wider batches take segment()
+        static constexpr int kDepth = NCH == 1 ? kCoopDepth : 1;
         T rval[kCoopDepth]; double rlen[kCoopDepth];
         template <int SLOT>
         __device__ __forceinline__ void segment_at(bool ok, int r, int e, int a, double len)
@@ -212,6 +213,7 @@ template <typename T, int NCH>
 struct AdjointOp {
     const T* y; T* grad; VolumeMap m; int ch0;
     struct Sink {
+        static constexpr int kDepth = 1;
         T* vol; int nvox; int ne, na; int nch;
         double w[NCH];
         template <int SLOT>
@@ -252,6 +254,7 @@ struct AdjointOp {
 struct CountOp {
     int32_t* count; unsigned long long* total;
     struct Sink {
+        static constexpr int kDepth = 1;
         int pr, pe, pa; int n;
         __device__ __forceinline__ void segment(int r, int e, int a, double)
         {
@@ -273,6 +276,7 @@ struct CountOp {
 struct TraceOp {
     int32_t* vox; double* seg_len; int32_t* count; int64_t max_seg;
     struct Sink {
+        static constexpr int kDepth = 1;
         int32_t* vox; double* len; int64_t max_seg;
         int pr, pe, pa; int64_t n;
         __device__ __forceinline__ void segment(int r, int e, int a, double l)
@@ -305,6 +309,7 @@ template <typename L>
 struct StoreOp {
     const int64_t* offsets; int32_t* vox; L* seg_len; int ne, na;
     struct Sink {
+        static constexpr int kDepth = 1;
         int32_t* vox; L* len; int ne, na;
         int cur; double acc; int64_t n;          // pending segment (consecutive identical voxels merge)
         __device__ __forceinline__ void segment(int r, int e, int a, double l)
@@ -335,6 +340,7 @@ struct StoreOp {
 struct EventTraceOp {
     int32_t* vox; double* ev_len; int32_t* count; int64_t max_ev;
     struct Sink {
+        static constexpr int kDepth = 1;
         int32_t* vox; double* len; int64_t max_ev;
         __device__ __forceinline__ void segment(int, int, int, double) {}
         template <int SLOT>
