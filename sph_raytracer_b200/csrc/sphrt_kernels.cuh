@@ -191,6 +191,7 @@ struct ForwardOp {
     }
     // warp-cooperative walker: every lane holds a partial sum of the same ray
     static constexpr bool kCoop = true, kEvents = false;
+    __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
     __device__ __forceinline__ void coop_end(int64_t ray, Sink& s, int lane, int) const
     {
         s.flush();
@@ -248,6 +249,17 @@ struct AdjointOp {
     __device__ __forceinline__ void end(int64_t, Sink&) const {}
     static constexpr bool kCoop = true, kEvents = false;
     __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
+    // a ray whose weights are all zero (masked measurements: loss.py projection_mask) adds nothing
+    __device__ __forceinline__ bool void_ray(int64_t ray) const
+    {
+        if (m.rays_per_vol > 0) return __ldg(y + ray) == T(0);
+        const int nch = (int)min((int64_t)NCH, m.n_vol - ch0);
+        bool zero = true;
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            if (c < nch) zero &= __ldg(y + (int64_t)(ch0 + c) * m.n_rays + ray) == T(0);
+        return zero;
+    }
 };
 
 // canonical segment bookkeeping shared by count / trace: consecutive identical voxels merge
@@ -357,6 +369,7 @@ struct EventTraceOp {
     }
     __device__ __forceinline__ void end(int64_t ray, Sink&) const { count[ray] = 0; }   // a miss
     static constexpr bool kCoop = true, kEvents = true;
+    __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
     __device__ __forceinline__ void coop_end(int64_t ray, Sink&, int lane, int n_events) const
     {
         if (lane == 0) count[ray] = n_events;
@@ -561,7 +574,7 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         int64_t start_index = 0;
         const uint32_t sel = in_mask != nullptr ? __ldg(in_mask + tile) : 0xffffffffu;
         if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
-        if (i < kr.n && ((sel >> lane) & 1u)) {
+        if (i < kr.n && ((sel >> lane) & 1u) && !op.void_ray(i)) {
             const Phase0Result r0 = coop_phase0<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
             cls = r0.cls; start_index = r0.start_index;
             ri0 = r0.ri[0]; ri1 = r0.ri[1]; ri2 = r0.ri[2]; ri3 = r0.ri[3]; ri4 = r0.ri[4]; ri5 = r0.ri[5];

@@ -301,3 +301,23 @@ def test_rays_with_a_snapped_leading_coefficient(S):
     _, bad_t = _compare_handled(cnt.reshape(-1).cpu().numpy(), vox.reshape(-1, ms, 3).cpu().numpy(),
                                 sl.reshape(-1, ms).cpu().numpy(), v0, s0, c0)
     assert len(bad_t) == 0, bad_t
+
+
+def test_masked_rays_are_skipped_in_the_adjoint(S, walker):
+    """Rays with zero weight (loss.py projection_mask) contribute nothing and are not walked."""
+    grid = S.SphericalGrid((40, 36, 48), size_r=(0.5, 3))
+    geom = S.ConeRectGeom((64, 48), (7.0, 1.0, 2.0), fov=(50, 50))
+    op = S.Operator(grid, geom)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    y = torch.rand(64, 48, generator=gen, device="cuda", dtype=torch.float64)
+    mask = (torch.rand(64, 48, generator=gen, device="cuda") > 0.5).double()
+    for mode in ("coop", "tracked"):
+        walker(mode)
+        full = op.T(y)
+        part = op.T(y * mask) + op.T(y * (1 - mask))
+        assert torch.allclose(full, part, rtol=1e-11, atol=1e-12)
+    ych = torch.stack([y * mask, torch.zeros_like(y), y])          # channels: zero only in some
+    walker("coop")
+    g3 = op.adjoint(ych, density_shape=(3,) + tuple(grid.shape))
+    assert torch.allclose(g3[0], op.T(y * mask), rtol=1e-11, atol=1e-12) and g3[1].abs().max() == 0
+    assert torch.allclose(g3[2], op.T(y), rtol=1e-11, atol=1e-12)
