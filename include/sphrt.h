@@ -155,6 +155,15 @@ int sphrt_trace_events(const sphrt_grid *grid, const sphrt_rays *rays, int64_t m
                        unsigned long long *stats,
                        void *scratch, int64_t scratch_bytes, void *stream);
 
+/* r_torch / e_torch / a_torch (raytracer.py:248-552) as trace_indices calls them (:83-88): the
+ * unsorted candidate table of every ray, K1 = 2(nr+1) + 2(ne+1) + (na+1) entries in the order
+ * [first radial roots | second radial roots | first cone roots | second cone roots | planes]:
+ * t (n_rays, K1) f64 distance (+inf: none), region (n_rays, K1) the reference's region value
+ * (-1 outside, -2 unchanged), geo (n_rays, K1) boundary index minus negative_crossing.
+ * Debug / parity export (the Python mirror's r_torch, e_torch, a_torch). */
+int sphrt_candidates(const sphrt_grid *grid, const sphrt_rays *rays, double *t, int32_t *region,
+                     int32_t *geo, void *stream);
+
 /* Which kernel walks the ordinary rays of this grid in sphrt_forward / sphrt_adjoint:
  * 1 = warp-cooperative walker (csrc/sphrt_coop.cuh; large grids), 0 = per-thread walker.
  * Both produce the same segments; the choice (grid size, overridable with the environment

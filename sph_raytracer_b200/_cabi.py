@@ -15,7 +15,7 @@ F32, F64 = 0, 1
 EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphrt_scratch_bytes",
            "sphrt_forward", "sphrt_adjoint", "sphrt_count_segments", "sphrt_trace_segments",
            "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind",
-           "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored")
+           "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates")
 
 
 class Grid(ctypes.Structure):
@@ -80,6 +80,8 @@ def load(path=None):
     lib.sphrt_forward_stored.argtypes = stored_args
     lib.sphrt_adjoint_stored.restype = c_int
     lib.sphrt_adjoint_stored.argtypes = stored_args
+    lib.sphrt_candidates.restype = c_int
+    lib.sphrt_candidates.argtypes = [P(Grid), P(Rays), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sphrt_walker_kind.restype = c_int
     lib.sphrt_walker_kind.argtypes = [P(Grid), c_int64]
     lib.sphrt_find_starts.restype = c_int

@@ -110,6 +110,23 @@ int sphrt_walker_kind(const sphrt_grid* grid, int64_t n_rays)
     return (plan_coop(*grid, n_rays).ok && want_coop(*grid)) ? 1 : 0;
 }
 
+int sphrt_candidates(const sphrt_grid* grid, const sphrt_rays* rays, double* t, int32_t* region,
+                     int32_t* geo, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays == 0) return SPHRT_OK;
+    if (!t || !region || !geo) return SPHRT_EINVAL;
+    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
+                   rays->start_cells};
+    const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t blocks = (rays->n_rays + kBlock - 1) / kBlock;
+    candidates_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(*grid, kr, t, region, geo);
+    return cuda_status();
+}
+
 int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32_t* out, void* stream)
 {
     int rc = check_grid(grid); if (rc) return rc;

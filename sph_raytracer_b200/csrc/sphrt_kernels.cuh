@@ -665,6 +665,44 @@ walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, 
     });
 }
 
+// Unsorted candidate table of the reference (trace_indices :83-122 before the sort): for every
+// ray [first radial roots | second radial roots | first cone roots | second cone roots | planes],
+// distance, region after the crossing and geometric index (boundary index - negative crossing).
+// Debug / parity export behind r_torch / e_torch / a_torch of the Python mirror.
+__global__ void candidates_kernel(sphrt_grid kg, KRays kr, double* t_out, int32_t* reg_out, int32_t* geo_out)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kr.n) return;
+    double x[3], d[3];
+    load_ray(kr, i, x, d);
+    RayConsts c;
+    ray_setup(c, x, d);
+    const int nr1 = g.nr + 1, ne1 = g.ne + 1, na1 = g.na + 1;
+    const int64_t K1 = 2 * nr1 + 2 * ne1 + na1;
+    double* t = t_out + i * K1;
+    int32_t* reg = reg_out + i * K1;
+    int32_t* geo = geo_out + i * K1;
+    for (int k = 0; k < nr1; k++) {
+        const Event a = radial_event(g, c, k, false), b = radial_event(g, c, k, true);
+        t[k] = a.t; reg[k] = a.region; geo[k] = a.geo;
+        t[nr1 + k] = b.t; reg[nr1 + k] = b.region; geo[nr1 + k] = b.geo;
+    }
+    for (int k = 0; k < ne1; k++) {
+        Event a, b;
+        cone_events(g, c, k, a, b);
+        const int o = 2 * nr1;
+        t[o + k] = a.t; reg[o + k] = a.region; geo[o + k] = a.geo;
+        t[o + ne1 + k] = b.t; reg[o + ne1 + k] = b.region; geo[o + ne1 + k] = b.geo;
+    }
+    for (int k = 0; k < na1; k++) {
+        const Event a = plane_event(g, c, k);
+        const int o = 2 * nr1 + 2 * ne1;
+        t[o + k] = a.t; reg[o + k] = a.region; geo[o + k] = a.geo;
+    }
+}
+
 __global__ void find_starts_kernel(sphrt_grid kg, int64_t n, const double* xs, int32_t* out)
 {
     extern __shared__ double sm_tables[];

@@ -20,7 +20,7 @@ import torch
 from . import _cabi
 from .geometry import ViewGeomCollection
 
-__all__ = ["Operator", "find_starts", "DEVICE", "FTYPE", "ITYPE"]
+__all__ = ["Operator", "find_starts", "r_torch", "e_torch", "a_torch", "DEVICE", "FTYPE", "ITYPE"]
 
 # module defaults, same names as the reference (raytracer.py:12-15)
 DEVICE = "cuda"
@@ -488,3 +488,68 @@ def find_starts(grid, xs, ftype=FTYPE, device=DEVICE):
         _cabi.check(lib.sphrt_find_starts(tables.c, flat.shape[0], flat.data_ptr(), out.data_ptr(),
                                           torch.cuda.current_stream(cdev).cuda_stream))
     return out.to(torch.int64).reshape((3,) + lead).to(pts.device)
+
+
+def _candidates(family, bounds, xs, rays, device):
+    """Candidate table of one boundary family for rays ``xs + t * rays`` (the CUDA extension's
+    ``sphrt_candidates`` on a grid whose other two families are dummies)."""
+    import types
+    lib = _cabi.load()
+    cdev = _compute_device(device)
+    b = torch.asarray(bounds, dtype=torch.float64).cpu().reshape(-1)
+    if len(b) == 1:
+        # one boundary = no voxel: evaluate next to a dummy second boundary and keep the first's
+        # columns; with a single boundary the reference maps region 0 to "outside" (:321, 464, 532)
+        t, reg, inds, neg = _candidates(family, torch.cat((b, b + 1.0)), xs, rays, device)
+        cols = [0] if family == "a" else [0, 2]
+        reg = reg[..., cols]
+        return t[..., cols], torch.where(reg == 0, -1, reg), inds[..., cols], neg[..., cols]
+    dummy = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    grid = types.SimpleNamespace(r_b=b if family == "r" else dummy, e_b=b if family == "e" else dummy,
+                                 a_b=b if family == "a" else dummy)
+    tables = _GridTables(grid, cdev)
+    xs = torch.asarray(xs, dtype=torch.float64)
+    rays = torch.asarray(rays, dtype=torch.float64)
+    shape = torch.broadcast_shapes(xs.shape, rays.shape)
+    lead = tuple(shape[:-1])
+    geom = types.SimpleNamespace(ray_starts=xs.broadcast_to(shape).reshape(-1, 3),
+                                 rays=rays.broadcast_to(shape).reshape(-1, 3))
+    r = _Rays(geom, cdev, tables)
+    k1 = 2 * (tables.nr + 1) + 2 * (tables.ne + 1) + (tables.na + 1)
+    t = torch.empty((r.n, k1), dtype=torch.float64, device=cdev)
+    reg = torch.empty((r.n, k1), dtype=torch.int32, device=cdev)
+    geo = torch.empty((r.n, k1), dtype=torch.int32, device=cdev)
+    with torch.cuda.device(cdev):
+        _cabi.check(lib.sphrt_candidates(tables.c, r.c, t.data_ptr(), reg.data_ptr(), geo.data_ptr(),
+                                         torch.cuda.current_stream(cdev).cuda_stream))
+    n1 = len(b)
+    o = {"r": 0, "e": 2 * (tables.nr + 1), "a": 2 * (tables.nr + 1) + 2 * (tables.ne + 1)}[family]
+    width = n1 if family == "a" else 2 * n1
+    sl = slice(o, o + width)
+    inds = torch.arange(n1, device=cdev).repeat(1 if family == "a" else 2)
+    t, reg, geo = t[:, sl], reg[:, sl].to(torch.int64), geo[:, sl].to(torch.int64)
+    neg = inds[None, :] - geo
+    out_dev = xs.device
+    return (t.reshape(lead + (width,)).to(out_dev), reg.reshape(lead + (width,)).to(out_dev),
+            inds.broadcast_to((r.n, width)).reshape(lead + (width,)).to(out_dev),
+            neg.reshape(lead + (width,)).to(out_dev))
+
+
+def r_torch(r, xs, rays, ftype=FTYPE, itype=ITYPE, device=DEVICE):
+    """Intersections with the concentric shells ``r`` (reference raytracer.py:248-325):
+    ``(t, regions, inds, negative_crossing)``, each ``(*num_rays, 2 * len(r))`` -- first roots
+    then second roots.  Evaluated by the CUDA extension with the arithmetic the operator uses
+    (the rays are normalised as ``trace_indices`` leaves them, Appendix B of SURVEY.md)."""
+    return _candidates("r", r, xs, rays, device)
+
+
+def e_torch(e, xs, rays, ftype=FTYPE, itype=ITYPE, device=DEVICE):
+    """Intersections with the elevation cones ``e`` (reference raytracer.py:328-468), same
+    layout as :func:`r_torch`; region -2 marks a glancing crossing."""
+    return _candidates("e", e, xs, rays, device)
+
+
+def a_torch(a_b, xs, rays, ftype=FTYPE, itype=ITYPE, device=DEVICE):
+    """Intersections with the azimuth half-planes ``a_b`` (reference raytracer.py:471-552):
+    ``(t, regions, inds, negative_crossing)``, each ``(*num_rays, len(a_b))``."""
+    return _candidates("a", a_b, xs, rays, device)
