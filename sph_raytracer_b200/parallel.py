@@ -4,7 +4,8 @@ The forward pass needs no communication (every rank integrates its own observati
 through a replicated volume); the adjoint scatter-adds into a rank-local gradient volume
 and finishes with ONE all-reduce (sum) of that small volume over NCCL / NVLink
 (SURVEY.md 8e).  For a dynamic volume sharded by observation the time-slices touched by
-different ranks are disjoint, so the same all-reduce simply assembles them.
+different ranks are disjoint, so the same all-reduce simply assembles them (``ShardedOperator``
+shards the time axis of a dynamic grid together with the observations).
 
 Works with any initialised ``torch.distributed`` backend (``nccl`` on GPUs; the host logic
 is exercised with ``gloo`` in the CPU tests).
@@ -41,20 +42,36 @@ def allreduce_gradient(grad, group=None):
     return grad
 
 
+def _time_slices(grid, n_t):
+    """A view of a dynamic grid with ``n_t`` time-slices (same spatial boundaries)."""
+    import copy
+    g = copy.copy(grid)
+    g.shape = type(grid.shape)(n_t, *grid.shape[1:]) if hasattr(grid.shape, "_fields") else (n_t, *grid.shape[1:])
+    return g
+
+
 class _ShardedIntegral(torch.autograd.Function):
     @staticmethod
     def forward(ctx, density, sop):
         ctx.sop = sop
         with torch.enable_grad():
-            d = density.detach().requires_grad_(True)
+            # dynamic volume: this rank integrates its own observations through their own
+            # time-slices (observation o reads slice o, reference raytracer.py:705-706)
+            d = (density[sop.lo:sop.hi] if sop.dynamic else density).detach().requires_grad_(True)
             y = sop.local(d)
         ctx.save_for_backward(d, y)
+        ctx.full_shape = density.shape
         return y.detach()
 
     @staticmethod
     def backward(ctx, grad_out):
         d, y = ctx.saved_tensors
         (g,) = torch.autograd.grad(y, d, grad_out)
+        if ctx.sop.dynamic:
+            # the ranks' time-slices are disjoint: the sum over ranks just assembles them
+            full = torch.zeros(ctx.full_shape, dtype=g.dtype, device=g.device)
+            full[ctx.sop.lo:ctx.sop.hi] = g
+            g = full
         return allreduce_gradient(g.contiguous(), ctx.sop.group), None
 
 
@@ -74,13 +91,23 @@ class ShardedOperator:
         self.rank, self.world, self.group = rank, world, group
         self.grid = grid
         self.geom, (self.lo, self.hi) = shard_collection(geoms, rank, world)
-        if grid.dynamic:
-            raise NotImplementedError("dynamic volumes: shard the time axis with the observations")
-        self.local = operator_cls(grid, self.geom, **kwargs)
+        self.dynamic = bool(getattr(grid, "dynamic", False))
+        local_grid = grid
+        if self.dynamic:
+            # the time axis is sharded with the observations: a grid with this rank's slices
+            if grid.shape[0] != len(geoms):
+                raise IndexError(f"{grid.shape[0]} time-slices cannot be sharded with {len(geoms)} observations")
+            local_grid = _time_slices(grid, self.hi - self.lo)
+        self.local = operator_cls(local_grid, self.geom, **kwargs)
         self.device = self.local.device
 
     def __call__(self, density):
         return _ShardedIntegral.apply(density, self)
 
     def T(self, line_integrations):
-        return allreduce_gradient(self.local.T(line_integrations), self.group)
+        g = self.local.T(line_integrations)
+        if self.dynamic:
+            full = torch.zeros(tuple(self.grid.shape), dtype=g.dtype, device=g.device)
+            full[self.lo:self.hi] = g
+            g = full
+        return allreduce_gradient(g, self.group)

@@ -172,6 +172,67 @@ def test_sharded_operator_gloo_world2():
         assert np.allclose(ty, grad)
 
 
+class _DynOp:
+    """CPU stand-in for a dynamic operator: observation o integrates time-slice o with a fixed
+    random matrix per ray."""
+
+    def __init__(self, grid, geom, **kw):
+        self.grid, self.geom, self.device = grid, geom, "cpu"
+        assert grid.shape[0] == len(geom.geoms)            # local time axis = local observations
+        g = torch.Generator().manual_seed(77)
+        A = torch.rand(4, 6, math.prod(grid.shape[1:]), generator=g, dtype=torch.float64)
+        self.A = torch.stack([A[o.tag] for o in geom.geoms])
+
+    def __call__(self, density):
+        return torch.einsum("orv,ov->or", self.A, density.reshape(len(self.geom.geoms), -1))
+
+    def T(self, y):
+        return torch.einsum("orv,or->ov", self.A, y).reshape(tuple(self.grid.shape))
+
+
+def _dyn_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = S.SphericalGrid((4, 2, 3, 4))                   # four time-slices
+    geoms = []
+    for k in range(4):
+        g = S.ViewGeom(torch.zeros(6, 3), torch.ones(6, 3)); g.tag = k
+        geoms.append(g)
+    sop = P.ShardedOperator(grid, S.ViewGeomCollection(*geoms), _DynOp)
+    x = (torch.arange(96, dtype=torch.float64) / 7).reshape(4, 2, 3, 4).requires_grad_(True)
+    y = sop(x)
+    w = torch.ones_like(y) * (rank + 1)
+    (y * w).sum().backward()
+    q.put((rank, sop.lo, sop.hi, y.detach().numpy(), x.grad.numpy(), sop.T(w).numpy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_dynamic_operator_gloo_world2():
+    """Dynamic volume: the time axis is sharded with the observations; the all-reduce assembles the
+    ranks' disjoint gradient slices."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dyn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(77)
+    A = torch.rand(4, 6, 24, generator=g, dtype=torch.float64)
+    x = (torch.arange(96, dtype=torch.float64) / 7).reshape(4, 24)
+    full = torch.einsum("orv,ov->or", A, x).numpy()
+    w_full = torch.cat([torch.ones(2, 6), 2 * torch.ones(2, 6)]).double()
+    grad = torch.einsum("orv,or->ov", A, w_full).reshape(4, 2, 3, 4).numpy()
+    for rank, lo, hi, y, gx, ty in res:
+        assert np.allclose(y, full[lo:hi])
+        assert np.allclose(gx, grad) and np.allclose(ty, grad)
+
+
 def test_start_cells_match_find_starts():
     """The host-side binning of start points (what sphrt_rays.start_cells carries) is the
     reference's find_starts: known answers of the reference's own tests, the C oracle on random
