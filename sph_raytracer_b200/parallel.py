@@ -42,11 +42,14 @@ def allreduce_gradient(grad, group=None):
     return grad
 
 
-def _time_slices(grid, n_t):
-    """A view of a dynamic grid with ``n_t`` time-slices (same spatial boundaries)."""
+def _time_slices(grid, lo, hi):
+    """A view of a dynamic grid restricted to time-slices [lo, hi) (same spatial boundaries)."""
     import copy
     g = copy.copy(grid)
-    g.shape = type(grid.shape)(n_t, *grid.shape[1:]) if hasattr(grid.shape, "_fields") else (n_t, *grid.shape[1:])
+    shape = (hi - lo, *grid.shape[1:])
+    g.shape = type(grid.shape)(*shape) if hasattr(grid.shape, "_fields") else shape
+    if getattr(grid, "t", None) is not None:
+        g.t = grid.t[lo:hi]
     return g
 
 
@@ -97,7 +100,7 @@ class ShardedOperator:
             # the time axis is sharded with the observations: a grid with this rank's slices
             if grid.shape[0] != len(geoms):
                 raise IndexError(f"{grid.shape[0]} time-slices cannot be sharded with {len(geoms)} observations")
-            local_grid = _time_slices(grid, self.hi - self.lo)
+            local_grid = _time_slices(grid, self.lo, self.hi)
         self.local = operator_cls(local_grid, self.geom, **kwargs)
         self.device = self.local.device
 
