@@ -265,18 +265,16 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     const int m = g.nr - rec.imin + 1;
     const int nR = 2 * m;
     const double tang = 1e-17 * (1.0 + c.nx2);
-    for (int k = lane; k < nR; k += 32) {
-        const bool out = k >= m;
-        const int i = out ? rec.imin + (k - m) : g.nr - k;
-        const double r = g.r_b()[i];
+    for (int k = lane; k < m; k += 32) {           // shell nr - k: both roots share the square root
+        const double r = g.r_b()[g.nr - k];
         const double r2 = r * r;
         const double arg = r2 - c.dperp2;
         const double t1c = sqrt(arg);
-        const double tt = out ? c.tc + t1c : c.tc - t1c;
         // inward roots enter shell i - 1, outward roots shell i (CoopLists::radial_region); when
         // tangent within rounding the reference decides from the sign of d.p: bail out
         if (!(arg >= tang + 1e-17 * r2)) bad = true;
-        tR[k] = tt;
+        tR[k] = c.tc - t1c;
+        tR[nR - 1 - k] = c.tc + t1c;
     }
     if (lane == 0) tR[nR] = SPHRT_INF;
     __syncwarp();
