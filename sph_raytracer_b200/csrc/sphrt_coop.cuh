@@ -59,7 +59,6 @@ enum { COOP_MISS = 0, COOP_RAY = 1, COOP_LISTED = 2, COOP_TRACKED = 3 };
 
 struct CoopRecord {           // what phase 1 needs to know about a ray (warp-uniform there)
     double d0, d1, d2, tc, dperp2, t_turn;
-    double nx2;               // |x|^2 as ray_setup rounds it
     int imin;                 // innermost shell reached
     int e_first, e_count, e_step;     // cone candidates e_first + k * e_step, k < e_count
     int e_mid;                // slot of the elevation buffer where the two runs meet
@@ -255,11 +254,7 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     c.x0 = x[0]; c.x1 = x[1]; c.x2 = x[2];
     c.d0 = rec.d0; c.d1 = rec.d1; c.d2 = rec.d2;
     c.tc = rec.tc; c.dperp2 = rec.dperp2;
-#ifdef SPHRT_X_NX2
-    c.nx2 = rec.nx2;
-#else
     { const double nx = norm3(c.x0, c.x1, c.x2); c.nx2 = nx * nx; }      // as ray_setup
-#endif
     c.dz2 = c.d2 * c.d2;
     c.dzxz = c.d2 * c.x2;
     c.dx = dot3(c.d0, c.d1, c.d2, c.x0, c.x1, c.x2);
@@ -273,9 +268,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     const int m = g.nr - rec.imin + 1;
     const int nR = 2 * m;
     const double tang = 1e-17 * (1.0 + c.nx2);
-#ifdef SPHRT_X_BUILD_ROLLED
-#pragma unroll 1
-#endif
     for (int k = lane; k < m; k += 32) {           // shell nr - k: both roots share the square root
         const double r = g.r_b()[g.nr - k];
         const double r2 = r * r;
@@ -337,9 +329,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
         }
         nUp = n;
     } else if (kMode != COOP_ALLCONES)
-#ifdef SPHRT_X_BUILD_ROLLED
-#pragma unroll 1
-#endif
     for (int k0 = 0; k0 < rec.e_count; k0 += 32) {
         const int k = k0 + lane;
         const int i = rec.e_first + k * rec.e_step;
@@ -395,9 +384,6 @@ __device__ __forceinline__ bool coop_build(const GridView& g, const CoopPlan& P,
     double* tA = reinterpret_cast<double*>(wbase + P.off_tA);
     int16_t* rA = reinterpret_cast<int16_t*>(wbase + P.off_rA) + 1;
     int nA = 0;
-#ifdef SPHRT_X_BUILD_ROLLED
-#pragma unroll 1
-#endif
     for (int k0 = 0; k0 < rec.a_count; k0 += 32) {
         const int k = k0 + lane;
         double t = SPHRT_INF;
@@ -501,9 +487,6 @@ __device__ __forceinline__ int coop_merge_ea(const CoopPlan& P, char* wbase, con
     double xv = *pE, yv = *pA;
     bool viol = (i > 0 && i < L.nE && pE[-1] > xv) || (j > 0 && j < L.nA && pA[-1] > yv);
     bool tx = xv <= yv;
-#ifdef SPHRT_X_MERGE_ROLLED
-#pragma unroll 1
-#endif
     for (int g = g0; g < g0 + c; g++) {             // same trip count in every lane: no divergence
         const double t = tx ? xv : yv;
         const bool live = g < n;                    // beyond the end the heads are stale memory
@@ -565,9 +548,7 @@ __device__ __forceinline__ void coop_segments(const CoopLists& L, const double* 
     }
     const int g_end = g0 + c;
     constexpr int kDepth = Sink::kDepth;           // 1 for sinks without loads to hide
-#ifdef SPHRT_X_SEG_ROLLED
-#pragma unroll 1
-#endif
+    // (left to the compiler's 4x unroll: rolled, the forward gathers lose their overlap, +9 %)
     while (g + kDepth <= g_end) {
         SPHRT_COOP_STEP(0)
         if constexpr (kDepth > 1) SPHRT_COOP_STEP(1)

@@ -505,11 +505,7 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 #define SPHRT_COOP_WARPS 16
 #endif
 constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
-#ifdef SPHRT_X_NX2
-constexpr int kCoopRecDoubles = 7;
-#else
 constexpr int kCoopRecDoubles = 6;
-#endif
 constexpr int64_t kCoopSplitRays = 4 << 20;    // from here on the all-cones rays get their own launch
 
 // phase 0 of the cooperative walker for one ray: load, set up, classify, plan; the float64 part of
@@ -535,9 +531,6 @@ __device__ __forceinline__ Phase0Result coop_phase0(const GridView& g, const KRa
         recd[0 * 32 + lane] = rec.d0; recd[1 * 32 + lane] = rec.d1; recd[2 * 32 + lane] = rec.d2;
         recd[3 * 32 + lane] = rec.tc; recd[4 * 32 + lane] = rec.dperp2;
         recd[5 * 32 + lane] = rec.t_turn;
-#ifdef SPHRT_X_NX2
-        recd[6 * 32 + lane] = c.nx2;
-#endif
         r.ri[0] = rec.imin | (rec.e_mid << 16);
         r.ri[1] = rec.e_first; r.ri[2] = rec.e_count * rec.e_step;
         r.ri[3] = rec.a_first; r.ri[4] = rec.a_count * rec.a_dir;
@@ -602,9 +595,6 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
             rec.d0 = recd[0 * 32 + j]; rec.d1 = recd[1 * 32 + j]; rec.d2 = recd[2 * 32 + j];
             rec.tc = recd[3 * 32 + j]; rec.dperp2 = recd[4 * 32 + j];
             rec.t_turn = recd[5 * 32 + j];
-#ifdef SPHRT_X_NX2
-            rec.nx2 = recd[6 * 32 + j];
-#endif
             const int im = __shfl_sync(0xffffffffu, ri0, j);
             rec.imin = im & 0xffff; rec.e_mid = im >> 16;
             rec.e_first = __shfl_sync(0xffffffffu, ri1, j);
