@@ -233,6 +233,19 @@ def test_sharded_dynamic_operator_gloo_world2():
         assert np.allclose(gx, grad) and np.allclose(ty, grad)
 
 
+def test_sharded_dynamic_needs_one_slice_per_observation():
+    """A dynamic volume is sharded along time with the observations: the counts must agree, and the
+    local grid keeps the spatial boundaries and this rank's time samples."""
+    grid = S.SphericalGrid((4, 2, 3, 4))
+    geoms = S.ViewGeomCollection(*[S.ViewGeom(torch.zeros(2, 3), torch.ones(2, 3)) for _ in range(3)])
+    with pytest.raises(IndexError):
+        P.ShardedOperator(grid, geoms, _DynOp, rank=0, world=1)
+    local = P._time_slices(grid, 1, 3)
+    assert tuple(local.shape) == (2, 2, 3, 4) and local.dynamic
+    assert local.shape.t == 2 and torch.equal(local.t, grid.t[1:3])
+    assert local.r_b is grid.r_b and tuple(grid.shape) == (4, 2, 3, 4)     # the original is untouched
+
+
 def test_start_cells_match_find_starts():
     """The host-side binning of start points (what sphrt_rays.start_cells carries) is the
     reference's find_starts: known answers of the reference's own tests, the C oracle on random
