@@ -165,7 +165,7 @@ def run_reference(args):
     if rank != 0:
         return
     cb = cpu_baseline(args.workload, steps=args.steps + args.warmup)
-    _, _, desc = workload(args.workload, n_obs=1)
+    _, _, desc = workload(args.workload, args.obs)          # the GPU arm's config; the sample is in cpu_baseline
     line = {"impl": "reference", "metric": "ray-segments/s fwd+adjoint", "value": cb["value"],
             "unit": "ray-segments/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
