@@ -159,6 +159,17 @@ def cpu_baseline(name, steps=1):
             "build_s": t_build}
 
 
+def reference_memory_gb(grid, n_rays):
+    """Bytes the reference needs for `n_rays` rays through `grid`: every ray owns
+    nvox_ray = 2(nr+1) + 2(ne+1) + (na+1) candidate crossings; the stored operator holds 3 int64
+    indices + 1 float64 length for each of them and the start point (regs / lens have nvox_ray + 1
+    slots), its estimator counts 6 x 8 B per candidate."""
+    nr, ne, na = (int(v) for v in tuple(grid.shape)[-3:])
+    nvox_ray = 2 * (nr + 1) + 2 * (ne + 1) + (na + 1)
+    return {"stored_operator": 32.0 * (nvox_ray + 1) * n_rays / 1e9,
+            "estimator": 48.0 * nvox_ray * n_rays / 1e9, "slots_per_ray": nvox_ray + 1}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port) as its own arm."""
     rank = int(os.environ.get("RANK", "0"))
@@ -370,6 +381,9 @@ def run_gpu(args):
             "walker": op.walker(),
             "clocks": clocks,
             "peak_memory_gb": peak_bytes / 1e9,
+            # what the reference keeps for the same rays (regs + lens, raytracer.py:17-45) and its own
+            # working-set estimator (examples/memory_usage.py:23-44), whole job
+            "reference_memory_gb": reference_memory_gb(grid, tot_rays),
             "operator_build_s": t_build,
         }
         # the bounds that are actually near: one L2 gather / one L2 fp32 reduction per
