@@ -376,8 +376,10 @@ def run_gpu(args):
                          "algorithmic_bytes": f"{per[0]} B/segment + {per[1]} B/ray + {per[2]} B/voxel"},
             "e2e": {"value": 2 * tot_seg / (e2e_step / 1e3), "unit": "ray-segments/s",
                     "ms_per_step": e2e_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            # per pass: ordinary-ray walker + sorted-cone-list pass (+ masked per-thread pass)
-            "gpu_launches": (6 if coop else 4) * args.steps,
+            # per pass: cooperative walker (two launches from 4 Mi rays on: ordinary + all-cones
+            # instantiation) + masked per-thread pass + sorted-cone-list pass; per-thread walker:
+            # dense pass + sorted-cone-list pass
+            "gpu_launches": ((8 if rays_r >= (4 << 20) else 6) if coop else 4) * args.steps,
             "walker": op.walker(),
             "clocks": clocks,
             "peak_memory_gb": peak_bytes / 1e9,
