@@ -246,6 +246,20 @@ def test_sharded_dynamic_needs_one_slice_per_observation():
     assert local.r_b is grid.r_b and tuple(grid.shape) == (4, 2, 3, 4)     # the original is untouched
 
 
+def test_reference_memory_estimate_known_answers():
+    """bench.py's figure for what the reference stores: 2.048 GB of regs / lens for configs[1]
+    (250 000 rays x 256 slots x 32 B, measured in BASELINE.md) and 3.06 GB from the reference's own
+    estimator (examples/memory_usage.py:23-44 at the README's parameters)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    m = bench.reference_memory_gb(S.SphericalGrid((50, 50, 50)), 50 * 50 * 100)
+    assert m["slots_per_ray"] == 256
+    assert m["stored_operator"] == pytest.approx(2.048)
+    assert m["estimator"] == pytest.approx(3.06)
+
+
 def test_start_cells_match_find_starts():
     """The host-side binning of start points (what sphrt_rays.start_cells carries) is the
     reference's find_starts: known answers of the reference's own tests, the C oracle on random
