@@ -507,6 +507,16 @@ walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_sme
 constexpr int kCoopMaxWarps = SPHRT_COOP_WARPS;
 constexpr int kCoopRecDoubles = 6;
 constexpr int64_t kCoopSplitRays = 4 << 20;    // from here on the all-cones rays get their own launch
+// SPHRT_COOP_SPLIT_RAYS in the environment overrides the threshold (tests force the two-launch
+// path on small cases; 0 = always split)
+inline int64_t coop_split_rays()
+{
+    const char* e = getenv("SPHRT_COOP_SPLIT_RAYS");
+    if (e == nullptr || *e == 0) return kCoopSplitRays;
+    char* end = nullptr;
+    const long long v = strtoll(e, &end, 10);
+    return (end == e || v < 0) ? kCoopSplitRays : (int64_t)v;
+}
 
 // phase 0 of the cooperative walker for one ray: load, set up, classify, plan; the float64 part of
 // the record goes to shared memory ([field][lane]), the integer part comes back in registers
@@ -572,7 +582,8 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
         int cls = COOP_MISS;
         int ri0 = 0, ri1 = 0, ri2 = 0, ri3 = 0, ri4 = 0, ri5 = 0;      // integer part of the record
         int64_t start_index = 0;
-        const uint32_t sel = in_mask != nullptr ? __ldg(in_mask + tile) : 0xffffffffu;
+        // (plain load: in_mask may be listed_mask itself, which this kernel writes)
+        const uint32_t sel = in_mask != nullptr ? in_mask[tile] : 0xffffffffu;
         if (sel == 0u) { if (lane == 0) listed_mask[tile] = 0u; continue; }
         if (i < kr.n && ((sel >> lane) & 1u) && !op.void_ray(i)) {
             const Phase0Result r0 = coop_phase0<kMode>(g, kr, P, i, lane, recd, &start_cache, table_ok);
@@ -944,7 +955,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
-            if (rays->n_rays < kCoopSplitRays) {
+            if (rays->n_rays < coop_split_rays()) {
                 rc = launch_coop<Op, COOP_BOTH>(cx, cl, op, nullptr, cx.counters, stats);
             } else {
                 rc = launch_coop<Op, COOP_ORDINARY>(cx, cl, op, nullptr, cx.counters, stats);
