@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = [os.path.join(CSRC, n) for n in ("sphrt_forward.cu", "sphrt_adjoint.cu", "sphrt_api.cu")]
 HEADERS = [os.path.join(CSRC, n) for n in ("sphrt_kernels.cuh", "sphrt_walker.cuh", "sphrt_fast.cuh",
-                                           "sphrt_coop.cuh")] + [os.path.join(HERE, "..", "include", "sphrt.h")]
+                                           "sphrt_coop.cuh", "sphrt_warp.cuh")] + [os.path.join(HERE, "..", "include", "sphrt.h")]
 LIB = os.path.join(HERE, "libsphrt.so")
 
 NVCC_FLAGS = [

@@ -27,11 +27,8 @@ const char* sphrt_error_string(int code)
 int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
 {
     if (grid == nullptr || grid->ne < 1 || n_rays < 0) return 0;
-    int64_t bytes = 2 * mask_bytes(n_rays) + 256;     // + tile counter of the cooperative walker
-    const ListPlan lp = plan_lists(*grid, n_rays);
-    if (lp.global_lists)
-        bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
-    return bytes;
+    // masks + counters + global cone lists (very large grids) + records of the warp walker
+    return scratch_bytes_before_recs(grid, n_rays) + warp_scratch_bytes(*grid, n_rays);
 }
 
 
@@ -100,7 +97,7 @@ int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t m
     rc = check_rays(rays); if (rc) return rc;
     if (max_ev < 1) return SPHRT_EINVAL;
     if (rays->n_rays > 0 && (!vox || !ev_len || !count)) return SPHRT_EINVAL;
-    const EventTraceOp op{vox, ev_len, count, max_ev};
+    const EventTraceOp op{vox, ev_len, count, max_ev, grid->nr};
     return launch_passes(grid, rays, op, scratch, scratch_bytes, stream, true, stats);
 }
 

@@ -29,7 +29,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "sphrt_coop.cuh"
+#include "sphrt_warp.cuh"
 
 using namespace sphrt;
 
@@ -124,6 +124,28 @@ struct VolumeMap {
     }
 };
 
+// predicated accumulate / gather of the warp walker's forward sink (see ForwardOp::WSink)
+__device__ __forceinline__ void fma_if(float& acc, float a, float b, unsigned p)
+{
+    asm("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q fma.rn.f32 %0, %1, %2, %0;\n}"
+        : "+f"(acc) : "f"(a), "f"(b), "r"(p));
+}
+__device__ __forceinline__ void fma_if(double& acc, double a, double b, unsigned p)
+{
+    asm("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q fma.rn.f64 %0, %1, %2, %0;\n}"
+        : "+d"(acc) : "d"(a), "d"(b), "r"(p));
+}
+__device__ __forceinline__ void ldg_if(float& v, const float* base, unsigned idx, unsigned p)
+{
+    asm volatile("{\n .reg .pred q;\n .reg .u64 a;\n setp.ne.u32 q, %3, 0;\n mad.wide.u32 a, %2, 4, %1;\n"
+                 " @q ld.global.nc.f32 %0, [a];\n}" : "+f"(v) : "l"(base), "r"(idx), "r"(p));
+}
+__device__ __forceinline__ void ldg_if(double& v, const double* base, unsigned idx, unsigned p)
+{
+    asm volatile("{\n .reg .pred q;\n .reg .u64 a;\n setp.ne.u32 q, %3, 0;\n mad.wide.u32 a, %2, 8, %1;\n"
+                 " @q ld.global.nc.f64 %0, [a];\n}" : "+d"(v) : "l"(base), "r"(idx), "r"(p));
+}
+
 template <typename T, int NCH>
 struct ForwardOp {
     const T* density; T* out; VolumeMap m; int ch0;
@@ -189,6 +211,72 @@ struct ForwardOp {
         for (int c = 0; c < NCH; c++)
             if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
     }
+    // second-generation warp walker (sphrt_warp.cuh): segments arrive as (flat voxel offset,
+    // length).  One channel: the gather of a segment is issued under its predicate and consumed two
+    // segments later under the same predicate (predicated inside inline PTX: written as C++ `if`s the
+    // compiler selects between old and new sums instead); float32 volumes accumulate value * length
+    // in float32 per lane (ten-odd terms; the reference itself rounds every product to float32 and
+    // sums in float32, raytracer.py:710-713), the 32 partial sums are added in float64.  Wider
+    // batches accumulate directly in float64.
+    struct WSink {
+        const T* vol; int nvox; int nch;
+        double acc[NCH];
+        T facc, pv[2], pl[2]; unsigned pk[2];
+        template <int SLOT>
+        __device__ __forceinline__ void seg(bool ok, unsigned idx, double len)
+        {
+            if constexpr (NCH == 1) {
+                fma_if(facc, pv[SLOT], pl[SLOT], pk[SLOT]);
+                pk[SLOT] = ok ? 1u : 0u; pl[SLOT] = (T)len;
+                ldg_if(pv[SLOT], vol, idx, pk[SLOT]);
+            } else {
+                if (ok) {
+#pragma unroll
+                    for (int c = 0; c < NCH; c++)
+                        if (c < nch) acc[c] = fma_rn((double)__ldg(vol + (size_t)c * nvox + idx), len, acc[c]);
+                }
+            }
+        }
+    };
+    __device__ __forceinline__ WSink wbegin(int64_t ray) const
+    {
+        WSink s;
+        s.vol = density + m.first_volume(ray, ch0) * m.nvox;
+        s.nvox = (int)m.nvox;
+        s.nch = m.rays_per_vol > 0 ? 1 : (int)min((int64_t)NCH, m.n_vol - ch0);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) s.acc[c] = 0.0;
+        s.facc = T(0); s.pk[0] = s.pk[1] = 0u; s.pl[0] = s.pl[1] = T(0); s.pv[0] = s.pv[1] = T(0);
+        return s;
+    }
+    __device__ __forceinline__ void wend(int64_t ray, WSink& s, int lane, int) const
+    {
+        if constexpr (NCH == 1) {
+            fma_if(s.facc, s.pv[0], s.pl[0], s.pk[0]);
+            fma_if(s.facc, s.pv[1], s.pl[1], s.pk[1]);
+            s.acc[0] = (double)s.facc;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            double a = s.acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            s.acc[c] = a;
+        }
+        if (lane != 0) return;
+        if (m.rays_per_vol > 0) { out[ray] = (T)s.acc[0]; return; }
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+            if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
+    }
+    // rays that never reach the grid are not walked at all: the result is zero-filled up front
+    int prefill(cudaStream_t st) const
+    {
+        if (m.rays_per_vol > 0) return (int)cudaMemsetAsync(out, 0, sizeof(T) * (size_t)m.n_rays, st);
+        const int64_t nch = min((int64_t)NCH, m.n_vol - ch0);
+        return (int)cudaMemsetAsync(out + (int64_t)ch0 * m.n_rays, 0, sizeof(T) * (size_t)(nch * m.n_rays), st);
+    }
+    int32_t* miss_count() const { return nullptr; }
     // warp-cooperative walker: every lane holds a partial sum of the same ray
     static constexpr bool kCoop = true, kEvents = false;
     __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
@@ -209,6 +297,21 @@ struct ForwardOp {
             if (c < s.nch) out[(int64_t)(ch0 + c) * m.n_rays + ray] = (T)s.acc[c];
     }
 };
+
+// red.global.add on a pointer the compiler can no longer see the address space of
+// (predicated inside the asm: a C++ `if` around it becomes a branch per segment)
+__device__ __forceinline__ void red_add_global_if(bool ok, float* p, float v)
+{
+    asm volatile("" :: "l"(p), "f"(v));          // value and address are formed outside the guard
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q red.global.add.f32 [%0], %1;\n}"
+                 :: "l"(p), "f"(v), "r"((unsigned)ok) : "memory");
+}
+__device__ __forceinline__ void red_add_global_if(bool ok, double* p, double v)
+{
+    asm volatile("" :: "l"(p), "d"(v));
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q red.global.add.f64 [%0], %1;\n}"
+                 :: "l"(p), "d"(v), "r"((unsigned)ok) : "memory");
+}
 
 template <typename T, int NCH>
 struct AdjointOp {
@@ -246,6 +349,38 @@ struct AdjointOp {
         }
         return s;
     }
+    struct WSink {
+        T* vol; int nvox; int nch;
+        double w[NCH];
+        template <int SLOT>
+        __device__ __forceinline__ void seg(bool ok, unsigned idx, double len)
+        {
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                red_add_global_if(ok && (NCH == 1 || (c < nch && w[c] != 0.0)),
+                                  vol + (size_t)c * nvox + idx, (T)(w[c] * len));
+        }
+    };
+    __device__ __forceinline__ WSink wbegin(int64_t ray) const
+    {
+        WSink s;
+        s.vol = grad + m.first_volume(ray, ch0) * m.nvox;
+        asm volatile("" : "+l"(s.vol));
+        s.nvox = (int)m.nvox;
+        if (m.rays_per_vol > 0) {
+            s.nch = 1;
+            s.w[0] = (double)__ldg(y + ray);
+        } else {
+            s.nch = (int)min((int64_t)NCH, m.n_vol - ch0);
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                s.w[c] = c < s.nch ? (double)__ldg(y + (int64_t)(ch0 + c) * m.n_rays + ray) : 0.0;
+        }
+        return s;
+    }
+    __device__ __forceinline__ void wend(int64_t, WSink&, int, int) const {}
+    int prefill(cudaStream_t) const { return 0; }
+    int32_t* miss_count() const { return nullptr; }
     __device__ __forceinline__ void end(int64_t, Sink&) const {}
     static constexpr bool kCoop = true, kEvents = false;
     __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
@@ -367,6 +502,30 @@ struct EventTraceOp {
     {
         return Sink{vox + 3 * ray * max_ev, ev_len + ray * max_ev, max_ev};
     }
+    struct WSink {
+        int32_t* vox; double* len; int64_t max_ev; int nr;
+        template <int SLOT>
+        __device__ __forceinline__ void seg(bool, unsigned, double) {}
+        // state of the second-generation walker: radial index, e * na + a (negative: outside)
+        __device__ __forceinline__ void event(int rank, int r, int sea, int na, double l)
+        {
+            if (rank >= max_ev) return;
+            if (r >= nr) r = -1;
+            const int e = sea < 0 ? -1 : sea / na, a = sea < 0 ? -1 : sea % na;
+            vox[3 * rank] = r; vox[3 * rank + 1] = e; vox[3 * rank + 2] = a; len[rank] = l;
+        }
+    };
+    int nr_for_wsink;
+    __device__ __forceinline__ WSink wbegin(int64_t ray) const
+    {
+        return WSink{vox + 3 * ray * max_ev, ev_len + ray * max_ev, max_ev, nr_for_wsink};
+    }
+    __device__ __forceinline__ void wend(int64_t ray, WSink&, int lane, int n_events) const
+    {
+        if (lane == 0) count[ray] = n_events;
+    }
+    int prefill(cudaStream_t) const { return 0; }
+    int32_t* miss_count() const { return count; }
     __device__ __forceinline__ void end(int64_t ray, Sink&) const { count[ray] = 0; }   // a miss
     static constexpr bool kCoop = true, kEvents = true;
     __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
@@ -639,6 +798,128 @@ walk_coop_kernel(sphrt_grid kg, KRays kr, Op op, CoopPlan P, const uint32_t* in_
     if (stats != nullptr && lane == 0) { atomicAdd(stats + 0, n_coop); atomicAdd(stats + 3, n_handed); }
 }
 
+
+// ---- second-generation warp walker (sphrt_warp.cuh) ---------------------------------------------
+// plan_warp_kernel: one thread per ray of a chunk.  Classifies the ray and, for the rays the warp
+// walker takes, appends an 80-byte record to a dense list; the other kinds are flagged in the two
+// bitmasks of the fallback passes exactly like walk_coop_kernel<COOP_ORDINARY> does.
+constexpr int kPlanBlock = 256;
+
+__global__ void __launch_bounds__(kPlanBlock)
+plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, PlanRec* recs,
+                 unsigned* n_recs, uint32_t* mask_listed, uint32_t* mask_tracked, int32_t* miss_count,
+                 unsigned long long* stats)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
+    bool table_ok = true;                  // the candidate ranges assume cos(e_b) descends
+    for (int k = threadIdx.x; k < g.ne; k += blockDim.x) table_ok &= g.cos_e()[k] > g.cos_e()[k + 1];
+    table_ok = __syncthreads_and(table_ok);
+    const int lane = threadIdx.x & 31;
+    const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // index inside the chunk
+    const int64_t i = base + li;
+    int cls = COOP_MISS;
+    CoopRecord rec;
+    RayConsts c;
+    int64_t start_index = 0;
+    if (li < n) {
+        double x[3], d[3];
+        load_ray(kr, i, x, d);
+        start_index = i / kr.rps;
+        ray_setup(c, x, d);
+        CoopStartCache cache{-1, true, true, 0, 0, 0};
+        cls = coop_plan_ray<COOP_ORDINARY>(g, c, x, P, start_index, kr.cells, cache, rec);
+        if (!table_ok && cls == COOP_RAY) cls = COOP_TRACKED;
+        if (cls == COOP_MISS && miss_count != nullptr) miss_count[i] = 0;
+    }
+    const uint32_t m_ray = __ballot_sync(0xffffffffu, cls == COOP_RAY);
+    const uint32_t m_listed = __ballot_sync(0xffffffffu, cls == COOP_LISTED);
+    const uint32_t m_tracked = __ballot_sync(0xffffffffu, cls == COOP_TRACKED);
+    unsigned slot0 = 0;
+    if (lane == 0 && li < n) {
+        mask_listed[i >> 5] = m_listed;
+        mask_tracked[i >> 5] = m_tracked;
+        if (m_ray) slot0 = atomicAdd(n_recs, (unsigned)__popc(m_ray));
+        if (stats != nullptr) {
+            if (m_tracked) atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
+        }
+    }
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (cls == COOP_RAY) {
+        PlanRec r;
+        r.d0 = rec.d0; r.d1 = rec.d1; r.d2 = rec.d2;
+        r.tc = rec.tc; r.dperp2 = rec.dperp2; r.t_turn = rec.t_turn; r.nx2 = c.nx2;
+        r.ray = (int32_t)li; r.start = (int32_t)start_index;
+        r.imin = (int16_t)rec.imin; r.e_mid = (int16_t)rec.e_mid;
+        r.e_first = (int16_t)rec.e_first; r.e_cs = (int16_t)(rec.e_count * rec.e_step);
+        r.a_first = (int16_t)rec.a_first; r.a_cd = (int16_t)(rec.a_count * rec.a_dir);
+        r.se0 = (int16_t)rec.se0; r.sa0 = (int16_t)rec.sa0;
+        store_plan_rec(recs + slot0 + __popc(m_ray & ((1u << lane) - 1u)), r);
+    }
+}
+
+#ifndef SPHRT_WARP_WARPS
+#define SPHRT_WARP_WARPS 24
+#endif
+constexpr int kWarpMaxWarps = SPHRT_WARP_WARPS;
+constexpr unsigned kWarpBatch = 8;              // records per hand-out
+
+// walk_warp_kernel: persistent warps take batches of planned rays from the dense record list.
+template <class Op>
+__global__ void __launch_bounds__(kWarpMaxWarps * 32, 1)
+walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPlan P,
+                 const PlanRec* __restrict__ recs, const unsigned* n_recs_p, int64_t ray_base,
+                 uint32_t* mask_tracked, unsigned* counter, unsigned long long* stats)
+{
+    extern __shared__ double sm_tables[];
+    const GridView g = stage_tables(kg, sm_tables);
+    // The lane index and the two shared-memory bases are passed through a shuffle so that ptxas
+    // keeps them in registers: it otherwise re-derives them from SR_TID.X / SR_CgaCtaId inside the
+    // loops (S2R has the latency of a shared-memory load).
+    int lane = threadIdx.x & 31;
+    uint32_t tab32 = smem_u32(sm_tables);
+    uint32_t wbase = tab32 + 8u * (uint32_t)P.table_doubles + (uint32_t)((threadIdx.x >> 5) * P.warp_bytes);
+    lane = __shfl_sync(0xffffffffu, lane, threadIdx.x);
+    tab32 = __shfl_sync(0xffffffffu, tab32, lane);
+    wbase = __shfl_sync(0xffffffffu, wbase, lane);
+    const Tab32 T(tab32, kg.nr, kg.ne, kg.na);
+    const unsigned n_recs = *n_recs_p;
+    unsigned n_ok = 0, n_fail = 0;
+    for (;;) {
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(counter, kWarpBatch);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_recs) break;
+        const unsigned e = b + kWarpBatch < n_recs ? b + kWarpBatch : n_recs;
+        // the records of the batch into L1 (80 bytes each, contiguous)
+        if (lane < 6) {
+            const char* p = reinterpret_cast<const char*>(recs + b) + 128 * lane;
+            if (p < reinterpret_cast<const char*>(recs + e)) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+        }
+        for (unsigned k = b; k < e; k++) {
+            const PlanRec R = load_plan_rec(recs + k);
+            const int64_t ray = ray_base + R.ray;
+            if (op.void_ray(ray)) continue;
+            typename Op::WSink sink = op.wbegin(ray);
+            const int nev = warp_walk_ray<Op::kEvents>(g, T, P, wbase, R, starts + 3 * (int64_t)R.start, lane, sink);
+            if (nev < 0) {
+                // a structural check failed: the per-thread walker takes the ray
+                if (lane == 0) atomicOr(mask_tracked + (ray >> 5), 1u << (ray & 31));
+                n_fail++;
+            } else {
+                op.wend(ray, sink, lane, nev);
+                n_ok++;
+            }
+            __syncwarp();              // the lists are reused by the next ray
+        }
+    }
+    if (stats != nullptr && lane == 0) {
+        atomicAdd(stats + 0, (unsigned long long)n_ok);
+        atomicAdd(stats + 2, (unsigned long long)n_fail);
+        atomicAdd(stats + 3, (unsigned long long)n_fail);
+    }
+}
+
 // pass B: persistent warps walk the rays flagged by pass A from a heap-sorted list of all cone
 // roots.  A warp takes one 32-ray mask word at a time (flagged rays come in runs along a
 // detector row, so its lanes fill up); each lane owns a [slot][thread] list column in shared
@@ -804,6 +1085,75 @@ CoopLaunch plan_coop(const sphrt_grid& g, int64_t n_rays)
     return c;
 }
 
+
+// ---- second-generation warp walker: shared-memory plan, chunking, selection -----------------------
+constexpr int kSmemMaxDynamic = 227 * 1024;
+constexpr int64_t kWarpChunkRays = 4 << 20;    // rays planned and walked per pair of launches
+
+struct WarpLaunch { WarpPlan P; CoopPlan caps; size_t smem; bool ok; };
+
+WarpLaunch plan_warp(const sphrt_grid& g)
+{
+    WarpLaunch w;
+    WarpPlan& P = w.P;
+    P.capR = 2 * (g.nr + 1);
+    P.capE = g.ne + 12;
+    P.capA = g.na / 2 + 4;
+    // a chord's colatitude varies by less than pi and its azimuth by at most pi
+    P.capEA = g.ne + g.na / 2 + 16;
+    P.padR = (P.capR + P.capEA + 31) / 32 + 2;
+    int off = 0;
+    auto take = [&off](int bytes) { const int o = off; off += (bytes + 7) / 8 * 8; return o; };
+    P.off_tE = take((P.capE + 1) * 8);
+    P.off_rE = take((P.capE + 2) * 4);
+    P.off_tA = take((P.capA + 1) * 8);
+    P.off_rA = take((P.capA + 2) * 4);
+    const int size_a = off;
+    P.off_tR = 0;
+    const int size_b = (P.capR + P.padR) * 8;
+    off = ((size_a > size_b ? size_a : size_b) + 15) / 16 * 16;
+    P.off_tEA = take((P.capEA + 1) * 8);
+    P.off_sEA = take((P.capEA + 2) * 4);
+    P.warp_bytes = (off + 15) / 16 * 16;
+    P.table_doubles = (int)table_doubles(g);
+    const int64_t tables = table_doubles(g) * (int64_t)sizeof(double);
+    int64_t warps = (kSmemMaxDynamic - tables) / P.warp_bytes;
+    if (warps > kWarpMaxWarps) warps = kWarpMaxWarps;
+    // packed states need nvox <= 2^30; the records hold 16-bit indices
+    // packed states: (nr + padding) * ne * na must stay below 2^30; the records hold 16-bit indices
+    w.ok = warps >= 4 && (int64_t)(g.nr + P.padR + 2) * g.ne * g.na <= (1LL << 30) &&
+           g.nr < 32000 && g.ne < 32000 && g.na < 32000;
+    P.warps = (int)(warps > 0 ? warps : 1);
+    w.smem = (size_t)(tables + (int64_t)P.warps * P.warp_bytes);
+    memset(&w.caps, 0, sizeof(w.caps));
+    w.caps.capE = P.capE; w.caps.capA = P.capA; w.caps.capR = P.capR; w.caps.capEA = P.capEA;
+    return w;
+}
+
+int64_t warp_chunk_rays()
+{
+    const char* e = getenv("SPHRT_WARP_CHUNK");
+    if (e != nullptr && *e) {
+        const long long v = strtoll(e, nullptr, 10);
+        if (v >= 32) return (int64_t)(v / 32 * 32);
+    }
+    return kWarpChunkRays;
+}
+
+// SPHRT_COOP_GEN = 2 (default) | 1 : generation of the cooperative walker that takes the ordinary rays
+bool want_warp_gen2()
+{
+    const char* e = getenv("SPHRT_COOP_GEN");
+    return !(e != nullptr && strcmp(e, "1") == 0);
+}
+
+int64_t warp_scratch_bytes(const sphrt_grid& g, int64_t n_rays)
+{
+    if (!plan_warp(g).ok) return 0;
+    const int64_t chunk = n_rays < warp_chunk_rays() ? n_rays : warp_chunk_rays();
+    return 256 + ((chunk + 31) / 32 * 32) * (int64_t)sizeof(PlanRec);
+}
+
 // SPHRT_WALKER = auto (default) | coop | tracked : which walker takes the ordinary rays.
 // auto: the cooperative walker pays off once a ray meets a few hundred boundaries.
 // SPHRT_COOP_LISTED=0 keeps the sorted-cone-list rays of the per-thread path in pass B (tests)
@@ -851,6 +1201,17 @@ int cuda_status()
     return SPHRT_OK;
 }
 
+
+// offset of the warp walker's record buffer inside the scratch area (after masks, counters, lists)
+int64_t scratch_bytes_before_recs(const sphrt_grid* grid, int64_t n_rays)
+{
+    int64_t bytes = 2 * mask_bytes(n_rays) + 256;
+    const ListPlan lp = plan_lists(*grid, n_rays);
+    if (lp.global_lists)
+        bytes += lp.blocks * lp.threads * 2 * (int64_t)(grid->ne + 1) * (int64_t)(sizeof(double) + sizeof(int));
+    return (bytes + 255) / 256 * 256;
+}
+
 template <class Op>
 int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const uint32_t* mask,
                   void* lists, size_t smem, const ListPlan& lp, unsigned long long* chunk_counter,
@@ -882,6 +1243,7 @@ struct PassContext {
                                          // [2] pass B  [3] cooperative all-cones tiles
     void* lists;                         // global cone lists of pass B (very large grids only)
     int64_t n_words;
+    PlanRec* recs;                       // records of the second-generation warp walker (one chunk)
 };
 
 template <class Op, int kMode>
@@ -892,6 +1254,39 @@ int launch_coop(const PassContext& cx, const CoopLaunch& cl, const Op& op, const
     walk_coop_kernel<Op, kMode><<<(unsigned)cl.blocks, cl.P.warps * 32, cl.smem, cx.st>>>(
         *cx.grid, cx.kr, op, cl.P, in_mask, cx.mask_listed, cx.mask_tracked, tile_counter, stats);
     return cuda_status();
+}
+
+
+// second-generation warp walker over every ray, chunk by chunk: plan -> walk
+template <class Op>
+int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsigned long long* stats)
+{
+    int rc = op.prefill(cx.st);
+    if (rc != 0) { sphrt_g_last_cuda_error = rc; return SPHRT_ECUDA; }
+    const size_t smem_plan = cx.smem_tables;
+    if (smem_plan > 48 * 1024)
+        cudaFuncSetAttribute(plan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
+    cudaFuncSetAttribute(walk_warp_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wl.smem);
+    unsigned* wc = reinterpret_cast<unsigned*>(cx.counters + 8);      // [0] records  [1] hand-out counter
+    const int64_t chunk = warp_chunk_rays();
+    const int sms = num_sms();
+    for (int64_t base = 0; base < cx.kr.n; base += chunk) {
+        const int64_t n = cx.kr.n - base < chunk ? cx.kr.n - base : chunk;
+        cudaMemsetAsync(wc, 0, 2 * sizeof(unsigned), cx.st);
+        const int64_t pb = (n + kPlanBlock - 1) / kPlanBlock;
+        plan_warp_kernel<<<(unsigned)pb, kPlanBlock, smem_plan, cx.st>>>(
+            *cx.grid, cx.kr, base, n, wl.caps, cx.recs, wc, cx.mask_listed, cx.mask_tracked,
+            op.miss_count(), stats);
+        rc = cuda_status();
+        if (rc != SPHRT_OK) return rc;
+        int64_t blocks = (n + (int64_t)wl.P.warps * kWarpBatch - 1) / ((int64_t)wl.P.warps * kWarpBatch);
+        if (blocks > sms) blocks = sms;
+        walk_warp_kernel<Op><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
+            *cx.grid, cx.kr.starts, op, wl.P, cx.recs, wc, base, cx.mask_tracked, wc + 1, stats);
+        rc = cuda_status();
+        if (rc != SPHRT_OK) return rc;
+    }
+    return SPHRT_OK;
 }
 
 template <class Op>
@@ -948,6 +1343,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     cx.counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
     cx.lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
     cx.n_words = (rays->n_rays + 31) / 32;
+    cx.recs = reinterpret_cast<PlanRec*>((char*)scratch + scratch_bytes_before_recs(grid, rays->n_rays));
     cudaMemsetAsync(cx.counters, 0, 4 * sizeof(unsigned long long), cx.st);
     const ListPlan lp = plan_lists(*grid, rays->n_rays);
     int rc;
@@ -955,7 +1351,14 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     if constexpr (Op::kCoop) {
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
-            if (rays->n_rays < coop_split_rays()) {
+            const WarpLaunch wl = plan_warp(*grid);
+            if (wl.ok && want_warp_gen2()) {
+                // ordinary rays: plan + walk kernels of sphrt_warp.cuh; then the all-cones rays,
+                // in place on their mask
+                rc = launch_warp(cx, wl, op, stats);
+                if (rc == SPHRT_OK)
+                    rc = launch_coop<Op, COOP_ALLCONES>(cx, cl, op, cx.mask_listed, cx.counters + 3, stats);
+            } else if (rays->n_rays < coop_split_rays()) {
                 rc = launch_coop<Op, COOP_BOTH>(cx, cl, op, nullptr, cx.counters, stats);
             } else {
                 rc = launch_coop<Op, COOP_ORDINARY>(cx, cl, op, nullptr, cx.counters, stats);

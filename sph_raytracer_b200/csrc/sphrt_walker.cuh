@@ -156,10 +156,18 @@ SPHRT_HD Event radial_event(const GridView& g, const RayConsts& c, int i, bool s
 // |aa| < tau snap (:376), delta is still unsnapped.
 struct ConeQuad { double aa, bb, cc, delta; };
 
+// (the same with the cone's cosine passed in: kernels that keep the tables behind plain
+// shared-memory addresses load it themselves)
+SPHRT_HD ConeQuad cone_quadratic_ce(const RayConsts& c, double ce);
+
 SPHRT_HD ConeQuad cone_quadratic(const GridView& g, const RayConsts& c, int i)
 {
+    return cone_quadratic_ce(c, g.cos_e()[i]);
+}
+
+SPHRT_HD ConeQuad cone_quadratic_ce(const RayConsts& c, double ce)
+{
     ConeQuad q;
-    const double ce = g.cos_e()[i];
     const double c2 = ce * ce;
     q.aa = c.dz2 - c2;
     q.bb = 2 * (c.dzxz - c.dx * c2);
@@ -181,7 +189,12 @@ SPHRT_HD void cone_roots(const ConeQuad& q, double delta, double& t1, double& t2
 
 // region a ray enters through cone i at distance t (:418-446, 464): sign of d . (p x phi_hat),
 // glancing crossings leave the index unchanged (-2)
+SPHRT_HD int cone_region_ne(int ne, const RayConsts& c, int i, double t, int* geo);
 SPHRT_HD int cone_region(const GridView& g, const RayConsts& c, int i, double t, int* geo)
+{
+    return cone_region_ne(g.ne, c, i, t, geo);
+}
+SPHRT_HD int cone_region_ne(int ne, const RayConsts& c, int i, double t, int* geo)
 {
     const double p0 = c.d0 * t + c.x0, p1 = c.d1 * t + c.x1, p2 = c.d2 * t + c.x2;
     const double n0 = -(p2 * p0), n1 = -(p2 * p1), n2 = fma_rn(p0, p0, p1 * p1);
@@ -190,17 +203,21 @@ SPHRT_HD int cone_region(const GridView& g, const RayConsts& c, int i, double t,
     *geo = i - neg;
     int region = i - neg;
     if (fabs(prod) < SPHRT_TAU) region = -2;
-    if (region == g.ne) region = -1;
+    if (region == ne) region = -1;
     return region;
 }
 
 // true if the root at distance t lies on the mirror nappe of cone i (:449-461)
-SPHRT_HD bool cone_shadow(const GridView& g, const RayConsts& c, int i, double t)
+SPHRT_HD bool cone_shadow_v(const RayConsts& c, double ce, double eb, double t)
 {
     const double p2 = c.d2 * t + c.x2;
-    bool shadow = (p2 >= 0) != (g.cos_e()[i] >= 0);
-    if (fabs(SPHRT_HALF_PI - g.e_b()[i]) < SPHRT_TAU) shadow = false;
+    bool shadow = (p2 >= 0) != (ce >= 0);
+    if (fabs(SPHRT_HALF_PI - eb) < SPHRT_TAU) shadow = false;
     return shadow;
+}
+SPHRT_HD bool cone_shadow(const GridView& g, const RayConsts& c, int i, double t)
+{
+    return cone_shadow_v(c, g.cos_e()[i], g.e_b()[i], t);
 }
 
 // region / shadow / NaN handling of one cone root (:418-466)

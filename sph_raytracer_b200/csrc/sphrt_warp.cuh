@@ -1,0 +1,422 @@
+// sphrt_warp.cuh -- warp-cooperative walker, second generation: the kernel that walks the ordinary
+// rays of large launches (every ray that starts outside the grid, off the cones / half-planes, and
+// has no snapped cone: 98-99 % of the rays that hit the grid at config 5).
+//
+// Same algorithm and the same exact arithmetic as sphrt_coop.cuh (three ascending event lists per
+// ray, evaluated by 32 lanes with the reference's formulas, verified, merged with two merge-path
+// stages -- the reference's sort + forward-fill + diff, raytracer.py:131-151), reorganised around
+// what ncu showed of that kernel (profiles/README.md, round 1d: 227 thread-instructions per segment
+// of which only ~20 % are float64 arithmetic, 16 warps per SM, instruction footprint twice the
+// instruction cache):
+//
+//   * PLANNING IS ITS OWN KERNEL (plan_warp_kernel, one thread per ray): classification, entry /
+//     exit / turning-point bins and candidate ranges go into an 80-byte record per ray that is
+//     walked; rays that never reach the grid produce nothing, the other kinds are flagged for the
+//     existing passes (all-cones run, per-thread walker, pass B).  The walking kernel is handed a
+//     dense list of records: no miss handling, no atan2, no binary searches in its instruction
+//     stream, and every warp-iteration is a ray with work.
+//   * SHARED MEMORY PER WARP IS 9 KB INSTEAD OF 13 KB at config 5: the radial list is built AFTER the
+//     elevation and azimuth lists have been merged and overlays them.  With <= 80 registers that is
+//     24 warps per SM instead of 16.
+//   * THE MERGE LOOPS CARRY PACKED STATE: elevation and azimuth regions are stored pre-multiplied
+//     (e * na, a) so that the merged list holds e * na + a, the radial state is the running offset
+//     r * ne * na, and ONE unsigned comparison of their sum against the voxel count replaces the
+//     three sign tests (an index outside the grid is a large negative number in either part); the
+//     radial list is padded with +inf so that the loop needs no end-of-sequence test; the gather is
+//     issued under its predicate and consumed one or two steps later under the same predicate.
+//
+// Rays whose lists fail verification are flagged for the per-thread walker exactly as before.
+#pragma once
+#include "sphrt_coop.cuh"
+
+namespace sphrt {
+
+constexpr int kInvalidState = -(1 << 30);            // packed state of an index outside the grid
+constexpr int kUnchangedState = kInvalidState - 1;   // glancing cone crossing: keep the previous one
+
+// Shared-memory layout of one warp (byte offsets from the warp's base), filled in by the host.
+struct WarpPlan {
+    int capR, padR, capE, capA, capEA;
+    int off_tE, off_rE, off_tA, off_rA;      // phase A: elevation / azimuth lists
+    int off_tR;                              // phase B: radial list, overlays phase A
+    int off_tEA, off_sEA;                    // merged elevation + azimuth list
+    int warp_bytes, warps, table_doubles;
+};
+
+// What the walking kernel needs to know about a ray (written by plan_warp_kernel).
+struct alignas(16) PlanRec {
+    double d0, d1, d2;        // direction as e_torch / a_torch see it (normalised three times)
+    double tc, dperp2;        // radial constants (r_torch, :288-289)
+    double t_turn;            // colatitude turning point (-inf: monotone along the chord)
+    double nx2;               // |x|^2 as e_torch computes it (norm()**2, :375)
+    int32_t ray, start;       // ray index relative to the chunk, row of `starts`
+    int16_t imin, e_mid;      // innermost shell reached; slot of the cone buffer where the runs meet
+    int16_t e_first, e_cs;    // cone candidates e_first + k * sign(e_cs), k < |e_cs|
+    int16_t a_first, a_cd;    // plane candidates a_first + k * sign(a_cd), k < |a_cd|
+    int16_t se0, sa0;         // elevation / azimuth state at the entry point
+};
+static_assert(sizeof(PlanRec) == 80, "PlanRec is loaded as five 16-byte words");
+
+__device__ __forceinline__ PlanRec load_plan_rec(const PlanRec* p)
+{
+    union { PlanRec r; int4 w[5]; } u;
+    const int4* s = reinterpret_cast<const int4*>(p);
+#pragma unroll
+    for (int k = 0; k < 5; k++) u.w[k] = __ldg(s + k);
+    return u.r;
+}
+
+__device__ __forceinline__ void store_plan_rec(PlanRec* p, const PlanRec& r)
+{
+    union { PlanRec r; int4 w[5]; } u;
+    u.r = r;
+    int4* d = reinterpret_cast<int4*>(p);
+#pragma unroll
+    for (int k = 0; k < 5; k++) d[k] = u.w[k];
+}
+
+// ---- shared memory behind plain 32-bit addresses ---------------------------------------------------
+// The lists and tables are addressed with 32-bit shared-window addresses and explicit ld/st.shared:
+// the compiler then keeps one address register per list (with generic pointers it re-derived the
+// window base -- S2UR SR_CgaCtaId -- inside the loops) and cannot turn the arithmetic list updates of
+// the merge loops back into pairs of predicated moves.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v)
+{
+    asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+
+// shared-window addresses of the boundary tables (GridView order): one base register, the other
+// tables at offsets that only depend on the grid shape (kernel parameters: uniform registers)
+struct Tab32 {
+    uint32_t r_b, e_b, cos_e, a_b, cos_a, sin_a;
+    int nr, ne, na;
+    __device__ __forceinline__ Tab32(uint32_t base, int nr_, int ne_, int na_)
+    {
+        nr = nr_; ne = ne_; na = na_;
+        r_b = base;
+        e_b = base + 8u * (uint32_t)(nr + 1);
+        cos_e = e_b + 8u * (uint32_t)(ne + 1);
+        a_b = cos_e + 8u * (uint32_t)(ne + 1);
+        cos_a = a_b + 8u * (uint32_t)(na + 1);
+        sin_a = cos_a + 8u * (uint32_t)(na + 1);
+    }
+};
+
+// number of X entries among the first g entries of merge(X, Y), X winning ties; X / Y are the
+// shared addresses of the lists; `steps` bisections (>= log2(min(nX, nY)) + 1, warp-uniform)
+__device__ __forceinline__ int warp_corank(uint32_t X, int nX, uint32_t Y, int nY, int g, int steps)
+{
+    int lo = g - nY > 0 ? g - nY : 0, hi = g < nX ? g : nX;
+    const uint32_t Yg = Y + 8u * (uint32_t)(g - 1);
+#pragma unroll 1
+    for (int s = 0; s < steps; s++) {
+        const int mid = (lo + hi) >> 1;
+        const bool open = lo < hi;
+        const bool take = lds_f64(X + 8u * mid) <= lds_f64(Yg - 8u * mid);   // stale values when !open
+        lo = (open && take) ? mid + 1 : lo;
+        hi = (open && !take) ? mid : hi;
+    }
+    return lo;
+}
+
+// Walk one planned ray with all 32 lanes.  Returns the number of merged events, or -1 if one of
+// the structural assumptions did not hold (nothing has been given to the sink then).
+template <bool kEvents, class Sink>
+__device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, const WarpPlan& P,
+                                             uint32_t wbase, const PlanRec& R, const double* xs, int lane,
+                                             Sink& sink)
+{
+    RayConsts c;
+    c.x0 = __ldg(xs); c.x1 = __ldg(xs + 1); c.x2 = __ldg(xs + 2);
+    c.d0 = R.d0; c.d1 = R.d1; c.d2 = R.d2;
+    c.tc = R.tc; c.dperp2 = R.dperp2; c.nx2 = R.nx2;
+    c.dz2 = c.d2 * c.d2;
+    c.dzxz = c.d2 * c.x2;
+    c.dx = dot3(c.d0, c.d1, c.d2, c.x0, c.x1, c.x2);
+    c.xz2 = c.x2 * c.x2;
+    c.r0 = c.r1 = c.r2 = 0.0;
+    bool bad = false;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int na = T.na;
+
+    // the chord inside the outermost shell: same expressions as the radial list below
+    double t_in, t_out;
+    {
+        const double rN = lds_f64(T.r_b + 8u * T.nr);
+        const double sN = sqrt(rN * rN - c.dperp2);
+        t_in = c.tc - sN; t_out = c.tc + sN;
+    }
+
+    // ---- elevation: candidates from the turning point outwards (as coop_build)
+    const uint32_t tEbuf = wbase + P.off_tE, rEbuf = wbase + P.off_rE + 4u;
+    const int e_count = R.e_cs < 0 ? -R.e_cs : R.e_cs, e_step = R.e_cs < 0 ? -1 : 1;
+    const int e_mid = R.e_mid;
+    int nDown = 0, nUp = 0;
+    bool unchanged = false;
+    for (int k0 = 0; k0 < e_count; k0 += 32) {
+        const int k = k0 + lane;
+        const int i = R.e_first + k * e_step;
+        double ta = SPHRT_INF, tb = SPHRT_INF;
+        int ra = 0, rb = 0;
+        if (k < e_count && i >= 0 && i <= T.ne) {
+            const double ce = lds_f64(T.cos_e + 8u * i), eb = lds_f64(T.e_b + 8u * i);
+            const ConeQuad q = cone_quadratic_ce(c, ce);
+            double t1, t2;
+            cone_roots(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
+            const bool v1 = t1 >= t_in && t1 <= t_out && !cone_shadow_v(c, ce, eb, t1);
+            const bool v2 = t2 >= t_in && t2 <= t_out && !cone_shadow_v(c, ce, eb, t2);
+            if (v1) ta = t1;
+            if (v2) { if (v1) tb = t2; else ta = t2; }
+            if (tb < ta) { const double tt = ta; ta = tb; tb = tt; }
+            if (tb == ta) tb = SPHRT_INF;                      // merged double root: one event
+            int geo;
+            if (ta < SPHRT_INF) ra = cone_region_ne(T.ne, c, i, ta, &geo);
+            // the candidates at both ends of the range are guards: they must stay silent
+            if ((k == 0 || k == e_count - 1) && ta < SPHRT_INF) bad = true;
+        }
+        if (__any_sync(SPHRT_FULL, tb < SPHRT_INF)) {           // cones crossed twice inside the chord
+            int geo;
+            if (tb < SPHRT_INF) rb = cone_region_ne(T.ne, c, i, tb, &geo);
+        }
+        const bool a_down = ta < R.t_turn;                      // first crossing (towards the turn)
+        const bool a_up = ta < SPHRT_INF && !a_down;
+        const bool b_up = tb < SPHRT_INF;
+        if (a_up && b_up) bad = true;                           // two crossings after the turn
+        const uint32_t md = __ballot_sync(SPHRT_FULL, a_down);
+        const uint32_t mu = __ballot_sync(SPHRT_FULL, a_up || b_up);
+        if (a_down) {
+            const int slot = e_mid - 1 - (nDown + __popc(md & lt_mask));
+            if (slot >= 0) {
+                sts_f64(tEbuf + 8u * slot, ta);
+                sts_s32(rEbuf + 4u * slot, ra >= 0 ? ra * na : (ra == -2 ? kUnchangedState : kInvalidState));
+            } else bad = true;
+            unchanged |= ra == -2;
+        }
+        if (a_up || b_up) {
+            const int slot = e_mid + nUp + __popc(mu & lt_mask);
+            const int rr = a_up ? ra : rb;
+            if (slot < P.capE) {
+                sts_f64(tEbuf + 8u * slot, a_up ? ta : tb);
+                sts_s32(rEbuf + 4u * slot, rr >= 0 ? rr * na : (rr == -2 ? kUnchangedState : kInvalidState));
+            } else bad = true;
+            unchanged |= rr == -2;
+        }
+        nDown += __popc(md); nUp += __popc(mu);
+    }
+    if (__any_sync(SPHRT_FULL, bad)) return -1;           // (also keeps the offsets below in range)
+    const uint32_t tE = tEbuf + 8u * (e_mid - nDown), rE = rEbuf + 4u * (e_mid - nDown);
+    const int nE = nDown + nUp;
+    if (lane == 0) {
+        sts_f64(tE + 8u * nE, SPHRT_INF);
+        sts_s32(rE - 4u, R.se0 >= 0 ? R.se0 * na : kInvalidState);
+    }
+
+    // ---- azimuth: planes in the direction of rotation (as coop_build)
+    const uint32_t tA = wbase + P.off_tA, rA = wbase + P.off_rA + 4u;
+    const int a_count = R.a_cd < 0 ? -R.a_cd : R.a_cd, a_dir = R.a_cd < 0 ? -1 : 1;
+    int nA = 0;
+    for (int k0 = 0; k0 < a_count; k0 += 32) {
+        const int k = k0 + lane;
+        double t = SPHRT_INF;
+        int geo = 0;
+        if (k < a_count) {
+            int pl = R.a_first + k * a_dir;                    // seam: plane na going up, 0 going down
+            if (pl > na) pl -= na;
+            if (pl < 0) pl += na;
+            if (pl == 0 || pl == na) {
+                // the seam: one half-plane the reference evaluates twice, earlier root wins
+                FastAzimuth::eval(g, c, pl, t_in, false, t, geo);
+                if (!(t <= t_out)) t = SPHRT_INF;
+            } else {
+                // plane_event() with the validity kept in a predicate.  Two exact identities are
+                // used: fma(0, z, y) == y for finite z (the reference's einsum carries the zero
+                // z-component of the plane normal, :508-513), and cross == den bit for bit
+                // ((-sa) * d0 == -(sa * d0))
+                const double ca = lds_f64(T.cos_a + 8u * pl), sa = lds_f64(T.sin_a + 8u * pl);
+                const double num = fma_rn(ca, c.x1, (-sa) * c.x0);
+                const double den = fma_rn(ca, c.d1, (-sa) * c.d0);
+                const double tt = -num / den;
+                geo = pl - (den < 0 ? 1 : 0);
+                const double px = tt * c.d0 + c.x0, py = tt * c.d1 + c.x1;
+                const bool valid = !(fabs(den) <= SPHRT_A_PARALLEL) && !(ca * px + sa * py < 0) &&
+                                   tt >= t_in && tt <= t_out;
+                if (valid) t = tt;
+            }
+            if (k == a_count - 1 && t < SPHRT_INF) bad = true;     // guard
+        }
+        const uint32_t mv = __ballot_sync(SPHRT_FULL, t < SPHRT_INF);
+        if (t < SPHRT_INF) {
+            const int slot = nA + __popc(mv & lt_mask);
+            const int reg = FastAzimuth::to_region(g, geo);
+            sts_f64(tA + 8u * slot, t);
+            sts_s32(rA + 4u * slot, reg >= 0 ? reg : kInvalidState);
+        }
+        nA += __popc(mv);
+    }
+    if (lane == 0) {
+        sts_f64(tA + 8u * nA, SPHRT_INF);
+        sts_s32(rA - 4u, R.sa0 >= 0 ? R.sa0 : kInvalidState);
+    }
+    const int nEA = nE + nA;
+    if (nEA > P.capEA) bad = true;
+    if (__any_sync(SPHRT_FULL, bad)) return -1;
+    __syncwarp();
+    // glancing crossings leave the elevation index unchanged: forward-fill (rare)
+    if (__any_sync(SPHRT_FULL, unchanged)) {
+        if (lane == 0) {
+#pragma unroll 1
+            for (int k = 0; k < nE; k++)
+                if (lds_s32(rE + 4u * k) == kUnchangedState) sts_s32(rE + 4u * k, lds_s32(rE + 4u * k - 4u));
+        }
+        __syncwarp();
+    }
+
+    // ---- stage 1: elevation + azimuth -> (t, packed state after the event); both lists are
+    // verified to ascend on the way (every entry is compared with its successor).  Written without
+    // data-dependent control flow: ONE counter (elevation events taken) gives all four addresses,
+    // and both heads are (re)loaded after every step.  The packed state is
+    // e * na + a + (imin - 1) * ne * na, so that stage 2 only adds |radial steps from the turning
+    // point| * ne * na to get the voxel offset.
+    const uint32_t tEA = wbase + P.off_tEA, sEA = wbase + P.off_sEA + 4u;
+    const int nena = T.ne * na;
+    const int base_r = (R.imin - 1) * nena;
+    {
+        const int c1 = (nEA + 31) >> 5;
+        const int g0 = lane * c1;
+        const int gs = g0 < nEA ? g0 : nEA;
+        const int nmin = nE < nA ? nE : nA;
+        int sE = warp_corank(tE, nE, tA, nA, gs, 32 - __clz(nmin > 0 ? nmin : 1));   // E events taken
+        const int j0 = gs - sE;
+        double xv = lds_f64(tE + 8u * sE), yv = lds_f64(tA + 8u * j0);
+        bool viol = (sE > 0 && sE < nE && lds_f64(tE + 8u * sE - 8u) > xv) ||
+                    (j0 > 0 && j0 < nA && lds_f64(tA + 8u * j0 - 8u) > yv);
+        // head of A after k steps: tA[gs + k - sE]; state of A: rA[gs + k - sE - 1]
+        uint32_t cAt = tA + 8u * gs, cAr = rA + 4u * gs - 4u;
+        uint32_t oT = tEA + 8u * g0, oS = sEA + 4u * g0;
+        const uint32_t rE1 = rE - 4u;
+        int left = nEA - g0;                           // live entries of this share (may be <= 0)
+        bool tx = xv <= yv;
+#define SPHRT_STAGE1_STEP(K)                                                                      \
+        {                                                                                         \
+            const double t = tx ? xv : yv;                                                        \
+            sE += tx ? 1 : 0;                                                                     \
+            xv = lds_f64(tE + 8u * sE);                                                           \
+            yv = lds_f64(cAt + 8u * ((K) + 1) - 8u * sE);                                         \
+            const int st = lds_s32(rE1 + 4u * sE) + lds_s32(cAr + 4u * ((K) + 1) - 4u * sE) + base_r; \
+            const bool live = (K) < left;          /* beyond the end the heads are stale memory */ \
+            viol |= live && (xv < t || yv < t);                                                   \
+            if (live) { sts_f64(oT + 8u * (K), t); sts_s32(oS + 4u * (K), st); }                  \
+            tx = xv <= yv;                                                                        \
+        }
+        int q = 0;
+        for (; q + 2 <= c1; q += 2) {                  // same trip count in every lane
+            SPHRT_STAGE1_STEP(0)
+            SPHRT_STAGE1_STEP(1)
+            cAt += 16u; cAr += 8u; oT += 16u; oS += 8u; left -= 2;
+        }
+        if (q < c1) SPHRT_STAGE1_STEP(0)
+#undef SPHRT_STAGE1_STEP
+        if (lane == 0) {
+            sts_f64(tEA + 8u * nEA, SPHRT_INF);
+            sts_s32(sEA - 4u, lds_s32(rE - 4u) + lds_s32(rA - 4u) + base_r);
+        }
+        if (__any_sync(SPHRT_FULL, viol)) return -1;
+    }
+    __syncwarp();                                      // phase A lists are dead from here on
+
+    // ---- radial list (overlays phase A): first roots of shells nr .. imin, then second roots of
+    // imin .. nr; padded with +inf so that the merge below may run past its end
+    const uint32_t tR = wbase + P.off_tR;
+    const int m = T.nr - R.imin + 1;
+    const int nR = 2 * m;
+    {
+        const double tang = 1e-17 * (1.0 + c.nx2);
+        for (int k = lane; k < m; k += 32) {           // both roots share the square root
+            const double r = lds_f64(T.r_b + 8u * (T.nr - k));
+            const double r2 = r * r;
+            const double arg = r2 - c.dperp2;
+            const double t1c = sqrt(arg);
+            // inward roots enter shell i - 1, outward roots shell i; when tangent within rounding
+            // the reference decides from the sign of d.p: bail out
+            if (!(arg >= tang + 1e-17 * r2)) bad = true;
+            sts_f64(tR + 8u * k, c.tc - t1c);
+            sts_f64(tR + 8u * (nR - 1 - k), c.tc + t1c);
+        }
+        for (int k = lane; k < P.padR; k += 32) sts_f64(tR + 8u * (nR + k), SPHRT_INF);
+    }
+    if (__any_sync(SPHRT_FULL, bad)) return -1;
+    __syncwarp();
+
+    // ---- stage 2: radial + (elevation, azimuth); every merged event starts one segment that ends
+    // at the next event (the reference's sort + forward-fill + diff, raytracer.py:131-151).
+    // ONE signed counter u = (radial events taken) - m gives everything: the radial head is
+    // tR[m + u], the other head is tEA[rank - m - u], and the radial index after the events taken
+    // is imin - 1 + |u| (inward events enter shells nr-1 .. imin-1, outward events imin .. nr), so
+    // the voxel offset is |u| * ne * na + packed state.  Before the entry and after the exit that
+    // is r = nr, below the innermost shell r = -1, and an (e, a) index outside the grid is a large
+    // negative number: one unsigned comparison with the voxel count tests all of it.  A length is
+    // never negative (the lists were verified); zero lengths (ties) add nothing.
+    const int n = nR + nEA;
+    {
+        const unsigned nvox = (unsigned)(T.nr * nena);
+        const int c2 = (n + 31) >> 5;
+        const int g0 = lane * c2;
+        const int gs = g0 < n ? g0 : n;
+        const int nmin = nR < nEA ? nR : nEA;
+        const int i0 = warp_corank(tR, nR, tEA, nEA, gs, 32 - __clz(nmin > 0 ? nmin : 1));
+        int u = i0 - m;
+        const uint32_t cR = tR + 8u * m;               // radial head: cR + 8 u
+        uint32_t cE = tEA + 8u * (gs - m);             // other head after k steps: cE + 8 k - 8 u
+        uint32_t cS = sEA + 4u * (gs - m) - 4u;        // its state:               cS + 4 k - 4 u
+        double xv = lds_f64(cR + 8u * u), yv = lds_f64(cE - 8u * u);
+        bool tx = xv <= yv;
+        double t = tx ? xv : yv;
+#define SPHRT_WARP_STEP(SLOT, K)                                                                  \
+        {                                                                                         \
+            u += tx ? 1 : 0;                                                                      \
+            xv = lds_f64(cR + 8u * u);                                                            \
+            yv = lds_f64(cE + 8u * ((K) + 1) - 8u * u);                                           \
+            const int sea = lds_s32(cS + 4u * ((K) + 1) - 4u * u);                                \
+            const unsigned idx = (unsigned)((u < 0 ? -u : u) * nena + sea);                       \
+            tx = xv <= yv;                                                                        \
+            const double tn = tx ? xv : yv;                                                       \
+            const double len = tn - t;                                                            \
+            const bool ok = idx < nvox;                                                           \
+            if constexpr (kEvents) {                                                              \
+                if (g0 + q + (K) < n) sink.event(g0 + q + (K), R.imin - 1 + (u < 0 ? -u : u), sea - base_r, na, \
+                                                 ok && len > 0 && tn < SPHRT_INF ? len : 0.0);    \
+            } else {                                                                              \
+                sink.template seg<SLOT>(ok, idx, len);                                            \
+            }                                                                                     \
+            t = tn;                                                                               \
+        }
+        int q = 0;
+        for (; q + 2 <= c2; q += 2) {
+            SPHRT_WARP_STEP(0, 0)
+            SPHRT_WARP_STEP(1, 1)
+            cE += 16u; cS += 8u;
+        }
+        if (q < c2) SPHRT_WARP_STEP(0, 0)
+#undef SPHRT_WARP_STEP
+    }
+    return n;
+}
+
+}  // namespace sphrt
