@@ -221,7 +221,7 @@ struct ForwardOp {
     struct WSink {
         const T* vol; int nvox; int nch;
         double acc[NCH];
-        T facc, pv[2], pl[2]; unsigned pk[2];
+        T facc, pv[kWarpDepth], pl[kWarpDepth]; unsigned pk[kWarpDepth];
         template <int SLOT>
         __device__ __forceinline__ void seg(bool ok, unsigned idx, double len)
         {
@@ -246,14 +246,16 @@ struct ForwardOp {
         s.nch = m.rays_per_vol > 0 ? 1 : (int)min((int64_t)NCH, m.n_vol - ch0);
 #pragma unroll
         for (int c = 0; c < NCH; c++) s.acc[c] = 0.0;
-        s.facc = T(0); s.pk[0] = s.pk[1] = 0u; s.pl[0] = s.pl[1] = T(0); s.pv[0] = s.pv[1] = T(0);
+        s.facc = T(0);
+#pragma unroll
+        for (int k = 0; k < kWarpDepth; k++) { s.pk[k] = 0u; s.pl[k] = T(0); s.pv[k] = T(0); }
         return s;
     }
     __device__ __forceinline__ void wend(int64_t ray, WSink& s, int lane, int) const
     {
         if constexpr (NCH == 1) {
-            fma_if(s.facc, s.pv[0], s.pl[0], s.pk[0]);
-            fma_if(s.facc, s.pv[1], s.pl[1], s.pk[1]);
+#pragma unroll
+            for (int k = 0; k < kWarpDepth; k++) fma_if(s.facc, s.pv[k], s.pl[k], s.pk[k]);
             s.acc[0] = (double)s.facc;
         }
 #pragma unroll
@@ -871,17 +873,32 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
                  const PlanRec* __restrict__ recs, const unsigned* n_recs_p, int64_t ray_base,
                  uint32_t* mask_tracked, unsigned* counter, unsigned long long* stats)
 {
-    extern __shared__ double sm_tables[];
-    const GridView g = stage_tables(kg, sm_tables);
-    // The lane index and the two shared-memory bases are passed through a shuffle so that ptxas
-    // keeps them in registers: it otherwise re-derives them from SR_TID.X / SR_CgaCtaId inside the
-    // loops (S2R has the latency of a shared-memory load).
+    extern __shared__ __align__(16) double sm_tables[];
+    // derived tables (Tab32): r_b^2 | { cos^2 e_b, shadow sign } | { cos a_b, sin a_b }
+    {
+        const int o_cone = (kg.nr + 2) & ~1, o_plane = o_cone + 2 * (kg.ne + 1);
+        for (int i = threadIdx.x; i <= kg.nr; i += blockDim.x) { const double r = __ldg(kg.r_b + i); sm_tables[i] = r * r; }
+        for (int i = threadIdx.x; i <= kg.ne; i += blockDim.x) {
+            const double ce = __ldg(kg.cos_e + i);
+            sm_tables[o_cone + 2 * i] = ce * ce;
+            sm_tables[o_cone + 2 * i + 1] = cone_shadow_sign(ce, __ldg(kg.e_b + i));
+        }
+        for (int i = threadIdx.x; i <= kg.na; i += blockDim.x) {
+            sm_tables[o_plane + 2 * i] = __ldg(kg.cos_a + i);
+            sm_tables[o_plane + 2 * i + 1] = __ldg(kg.sin_a + i);
+        }
+        __syncthreads();
+    }
+    // The lane index, its mask and the two shared-memory bases are passed through a shuffle so that
+    // ptxas keeps them in registers: it otherwise re-derives them from SR_TID.X / SR_CgaCtaId
+    // inside the loops (S2R has the latency of a shared-memory load).
     int lane = threadIdx.x & 31;
     uint32_t tab32 = smem_u32(sm_tables);
     uint32_t wbase = tab32 + 8u * (uint32_t)P.table_doubles + (uint32_t)((threadIdx.x >> 5) * P.warp_bytes);
     lane = __shfl_sync(0xffffffffu, lane, threadIdx.x);
     tab32 = __shfl_sync(0xffffffffu, tab32, lane);
     wbase = __shfl_sync(0xffffffffu, wbase, lane);
+    const uint32_t lt_mask = __shfl_sync(0xffffffffu, (1u << lane) - 1u, lane);
     const Tab32 T(tab32, kg.nr, kg.ne, kg.na);
     const unsigned n_recs = *n_recs_p;
     unsigned n_ok = 0, n_fail = 0;
@@ -901,7 +918,7 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
             const int64_t ray = ray_base + R.ray;
             if (op.void_ray(ray)) continue;
             typename Op::WSink sink = op.wbegin(ray);
-            const int nev = warp_walk_ray<Op::kEvents>(g, T, P, wbase, R, starts + 3 * (int64_t)R.start, lane, sink);
+            const int nev = warp_walk_ray<Op::kEvents>(T, P, wbase, R, starts + 3 * (int64_t)R.start, lane, lt_mask, sink);
             if (nev < 0) {
                 // a structural check failed: the per-thread walker takes the ray
                 if (lane == 0) atomicOr(mask_tracked + (ray >> 5), 1u << (ray & 31));
@@ -1115,8 +1132,8 @@ WarpLaunch plan_warp(const sphrt_grid& g)
     P.off_tEA = take((P.capEA + 1) * 8);
     P.off_sEA = take((P.capEA + 2) * 4);
     P.warp_bytes = (off + 15) / 16 * 16;
-    P.table_doubles = (int)table_doubles(g);
-    const int64_t tables = table_doubles(g) * (int64_t)sizeof(double);
+    P.table_doubles = Tab32::doubles(g.nr, g.ne, g.na);        // the walking kernel's own tables
+    const int64_t tables = P.table_doubles * (int64_t)sizeof(double);
     int64_t warps = (kSmemMaxDynamic - tables) / P.warp_bytes;
     if (warps > kWarpMaxWarps) warps = kWarpMaxWarps;
     // packed states need nvox <= 2^30; the records hold 16-bit indices

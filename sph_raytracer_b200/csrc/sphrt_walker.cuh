@@ -165,10 +165,15 @@ SPHRT_HD ConeQuad cone_quadratic(const GridView& g, const RayConsts& c, int i)
     return cone_quadratic_ce(c, g.cos_e()[i]);
 }
 
+SPHRT_HD ConeQuad cone_quadratic_c2(const RayConsts& c, double c2);
 SPHRT_HD ConeQuad cone_quadratic_ce(const RayConsts& c, double ce)
 {
+    return cone_quadratic_c2(c, ce * ce);
+}
+// (... or its square: tables of cos^2 hold the same product)
+SPHRT_HD ConeQuad cone_quadratic_c2(const RayConsts& c, double c2)
+{
     ConeQuad q;
-    const double c2 = ce * ce;
     q.aa = c.dz2 - c2;
     q.bb = 2 * (c.dzxz - c.dx * c2);
     q.cc = c.xz2 - c.nx2 * c2;
@@ -183,6 +188,21 @@ SPHRT_HD void cone_roots(const ConeQuad& q, double delta, double& t1, double& t2
     const double sq = sqrt(delta);
     t1 = (-q.bb + sq) / (2 * q.aa);
     t2 = (-q.bb - sq) / (2 * q.aa);
+    if (q.aa == 0 && !(fabs(q.bb) < SPHRT_TAU)) { t1 = -q.cc / q.bb; t2 = SPHRT_INF; }
+    if (q.aa == 0 && q.bb == 0 && q.cc == 0) { t1 = SPHRT_INF; t2 = SPHRT_INF; }
+}
+
+// cone_roots() for the GPU's warp walkers: a negative (or NaN) discriminant does not go through
+// sqrt and the two divisions -- their NaN slow paths cost a warp ~100 instructions for one lane, and
+// the guard candidates at the ends of every cone range have exactly that -- the roots are NaN as in
+// the reference (sqrt of a negative number, :385-386).  Same results as cone_roots().
+SPHRT_HD void cone_roots_guarded(const ConeQuad& q, double delta, double& t1, double& t2)
+{
+    const bool none = !(delta >= 0);
+    const double sq = sqrt(none ? 0.0 : delta);
+    t1 = (-q.bb + sq) / (2 * q.aa);
+    t2 = (-q.bb - sq) / (2 * q.aa);
+    if (none) { t1 = __builtin_nan(""); t2 = __builtin_nan(""); }
     if (q.aa == 0 && !(fabs(q.bb) < SPHRT_TAU)) { t1 = -q.cc / q.bb; t2 = SPHRT_INF; }
     if (q.aa == 0 && q.bb == 0 && q.cc == 0) { t1 = SPHRT_INF; t2 = SPHRT_INF; }
 }
@@ -215,6 +235,18 @@ SPHRT_HD bool cone_shadow_v(const RayConsts& c, double ce, double eb, double t)
     if (fabs(SPHRT_HALF_PI - eb) < SPHRT_TAU) shadow = false;
     return shadow;
 }
+// the same from a per-cone sign: 0 for the cones exempt by |e - pi/2| < tau, else +1 / -1 for
+// cos e >= 0 / < 0
+SPHRT_HD bool cone_shadow_sgn(const RayConsts& c, double sgn, double t)
+{
+    const double p2 = c.d2 * t + c.x2;
+    return (p2 >= 0) ? (sgn < 0) : (sgn > 0);
+}
+SPHRT_HD double cone_shadow_sign(double ce, double eb)
+{
+    if (fabs(SPHRT_HALF_PI - eb) < SPHRT_TAU) return 0.0;
+    return ce >= 0 ? 1.0 : -1.0;
+}
 SPHRT_HD bool cone_shadow(const GridView& g, const RayConsts& c, int i, double t)
 {
     return cone_shadow_v(c, g.cos_e()[i], g.e_b()[i], t);
@@ -231,10 +263,14 @@ SPHRT_HD Event cone_event(const GridView& g, const RayConsts& c, int i, double t
 }
 
 // ---- azimuth family (a_torch :505-550): the single root of half-plane i -------------------
+SPHRT_HD Event plane_event_v(double ca, double sa, const RayConsts& c, int i, int na, int wrap);
 SPHRT_HD Event plane_event(const GridView& g, const RayConsts& c, int i)
 {
+    return plane_event_v(g.cos_a()[i], g.sin_a()[i], c, i, g.na, g.wrap);
+}
+SPHRT_HD Event plane_event_v(double ca, double sa, const RayConsts& c, int i, int na, int wrap)
+{
     Event ev;
-    const double ca = g.cos_a()[i], sa = g.sin_a()[i];
     const double num = fma_rn(0.0, c.x2, fma_rn(ca, c.x1, (-sa) * c.x0));
     const double den = fma_rn(0.0, c.d2, fma_rn(ca, c.d1, (-sa) * c.d0));
     double t = -num / den;
@@ -243,8 +279,8 @@ SPHRT_HD Event plane_event(const GridView& g, const RayConsts& c, int i)
     const int neg = cross < 0;
     ev.geo = i - neg;                      // -1 .. na ; -1 and na are the gap sector
     int region = ev.geo;
-    if (g.wrap) { region %= g.na; if (region < 0) region += g.na; }
-    else if (region == g.na) region = -1;
+    if (wrap) { region %= na; if (region < 0) region += na; }
+    else if (region == na) region = -1;
     const double px = t * c.d0 + c.x0, py = t * c.d1 + c.x1;
     if (ca * px + sa * py < 0) t = SPHRT_INF;
     ev.region = region;

@@ -31,6 +31,11 @@
 
 namespace sphrt {
 
+#ifndef SPHRT_WARP_DEPTH
+#define SPHRT_WARP_DEPTH 4
+#endif
+constexpr int kWarpDepth = SPHRT_WARP_DEPTH;         // gathers in flight per lane in the segment loop: 2 or 4
+
 constexpr int kInvalidState = -(1 << 30);            // packed state of an index outside the grid
 constexpr int kUnchangedState = kInvalidState - 1;   // glancing cone crossing: keep the previous one
 
@@ -102,20 +107,31 @@ __device__ __forceinline__ void sts_s32(uint32_t a, int v)
     asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 }
 
-// shared-window addresses of the boundary tables (GridView order): one base register, the other
-// tables at offsets that only depend on the grid shape (kernel parameters: uniform registers)
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double& v0, double& v1)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
+
+// Tables of the walking kernel in shared memory, derived once per block from the grid's boundary
+// tables (same products as the per-ray code would form, so nothing changes numerically):
+//   r2   (nr + 1, padded to an even count)  r_b^2
+//   cone (ne + 1 pairs)   { cos^2 e_b, sign: 0 for cones exempt from the shadow test by
+//                           |e_b - pi/2| < tau (raytracer.py:449-461), else +1 / -1 for cos e_b >= 0 / < 0 }
+//   plane (na + 1 pairs)  { cos a_b, sin a_b }
+// One base register; the other tables sit at offsets that only depend on the grid shape.
 struct Tab32 {
-    uint32_t r_b, e_b, cos_e, a_b, cos_a, sin_a;
+    uint32_t r2, cone, plane;
     int nr, ne, na;
+    __host__ __device__ static int doubles(int nr, int ne, int na)
+    {
+        return ((nr + 2) & ~1) + 2 * (ne + 1) + 2 * (na + 1);
+    }
     __device__ __forceinline__ Tab32(uint32_t base, int nr_, int ne_, int na_)
     {
         nr = nr_; ne = ne_; na = na_;
-        r_b = base;
-        e_b = base + 8u * (uint32_t)(nr + 1);
-        cos_e = e_b + 8u * (uint32_t)(ne + 1);
-        a_b = cos_e + 8u * (uint32_t)(ne + 1);
-        cos_a = a_b + 8u * (uint32_t)(na + 1);
-        sin_a = cos_a + 8u * (uint32_t)(na + 1);
+        r2 = base;
+        cone = base + 8u * (uint32_t)((nr + 2) & ~1);
+        plane = cone + 16u * (uint32_t)(ne + 1);
     }
 };
 
@@ -138,9 +154,26 @@ __device__ __forceinline__ int warp_corank(uint32_t X, int nX, uint32_t Y, int n
 
 // Walk one planned ray with all 32 lanes.  Returns the number of merged events, or -1 if one of
 // the structural assumptions did not hold (nothing has been given to the sink then).
+// the seam of a full-circle grid: planes 0 and na are one half-plane that the reference evaluates
+// twice (with table values that differ in the last bits); the earlier root not behind t_now wins
+// (FastAzimuth::eval of sphrt_fast.cuh on the walking kernel's own tables)
+__device__ __forceinline__ void warp_seam_plane(const Tab32& T, const RayConsts& c, int i, double t_now,
+                                              double& t, int& geo)
+{
+    double ca, sa;
+    lds_f64x2(T.plane + 16u * i, ca, sa);
+    Event ev = plane_event_v(ca, sa, c, i, T.na, 1);
+    lds_f64x2(T.plane + 16u * (T.na - i), ca, sa);
+    const Event tw = plane_event_v(ca, sa, c, T.na - i, T.na, 1);
+    const bool ev_ok = !(ev.t < t_now), tw_ok = !(tw.t < t_now);
+    if (tw_ok && (!ev_ok || tw.t < ev.t)) ev = tw;
+    t = ev.t < t_now ? SPHRT_INF : ev.t;
+    geo = ev.geo;
+}
+
 template <bool kEvents, class Sink>
-__device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, const WarpPlan& P,
-                                             uint32_t wbase, const PlanRec& R, const double* xs, int lane,
+__device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, uint32_t wbase,
+                                             const PlanRec& R, const double* xs, int lane, uint32_t lt_mask,
                                              Sink& sink)
 {
     RayConsts c;
@@ -153,14 +186,12 @@ __device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, 
     c.xz2 = c.x2 * c.x2;
     c.r0 = c.r1 = c.r2 = 0.0;
     bool bad = false;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const int na = T.na;
 
     // the chord inside the outermost shell: same expressions as the radial list below
     double t_in, t_out;
     {
-        const double rN = lds_f64(T.r_b + 8u * T.nr);
-        const double sN = sqrt(rN * rN - c.dperp2);
+        const double sN = sqrt(lds_f64(T.r2 + 8u * T.nr) - c.dperp2);
         t_in = c.tc - sN; t_out = c.tc + sN;
     }
 
@@ -170,55 +201,59 @@ __device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, 
     const int e_mid = R.e_mid;
     int nDown = 0, nUp = 0;
     bool unchanged = false;
-    for (int k0 = 0; k0 < e_count; k0 += 32) {
-        const int k = k0 + lane;
-        const int i = R.e_first + k * e_step;
-        double ta = SPHRT_INF, tb = SPHRT_INF;
-        int ra = 0, rb = 0;
-        if (k < e_count && i >= 0 && i <= T.ne) {
-            const double ce = lds_f64(T.cos_e + 8u * i), eb = lds_f64(T.e_b + 8u * i);
-            const ConeQuad q = cone_quadratic_ce(c, ce);
-            double t1, t2;
-            cone_roots(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
-            const bool v1 = t1 >= t_in && t1 <= t_out && !cone_shadow_v(c, ce, eb, t1);
-            const bool v2 = t2 >= t_in && t2 <= t_out && !cone_shadow_v(c, ce, eb, t2);
-            if (v1) ta = t1;
-            if (v2) { if (v1) tb = t2; else ta = t2; }
-            if (tb < ta) { const double tt = ta; ta = tb; tb = tt; }
-            if (tb == ta) tb = SPHRT_INF;                      // merged double root: one event
-            int geo;
-            if (ta < SPHRT_INF) ra = cone_region_ne(T.ne, c, i, ta, &geo);
-            // the candidates at both ends of the range are guards: they must stay silent
-            if ((k == 0 || k == e_count - 1) && ta < SPHRT_INF) bad = true;
+    {
+        int k = lane, i = R.e_first + lane * e_step;
+        const int i_step = 32 * e_step;
+#pragma unroll 1
+        for (; __any_sync(SPHRT_FULL, k < e_count); k += 32, i += i_step) {
+            double ta = SPHRT_INF, tb = SPHRT_INF;
+            int ra = 0, rb = 0;
+            if (k < e_count && i >= 0 && i <= T.ne) {
+                double c2, sgn;
+                lds_f64x2(T.cone + 16u * i, c2, sgn);
+                const ConeQuad q = cone_quadratic_c2(c, c2);
+                double t1, t2;
+                cone_roots_guarded(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
+                const bool v1 = t1 >= t_in && t1 <= t_out && !cone_shadow_sgn(c, sgn, t1);
+                const bool v2 = t2 >= t_in && t2 <= t_out && !cone_shadow_sgn(c, sgn, t2);
+                if (v1) ta = t1;
+                if (v2) { if (v1) tb = t2; else ta = t2; }
+                if (tb < ta) { const double tt = ta; ta = tb; tb = tt; }
+                if (tb == ta) tb = SPHRT_INF;                      // merged double root: one event
+                int geo;
+                if (ta < SPHRT_INF) ra = cone_region_ne(T.ne, c, i, ta, &geo);
+                // the candidates at both ends of the range are guards: they must stay silent
+                if ((k == 0 || k == e_count - 1) && ta < SPHRT_INF) bad = true;
+            }
+            if (__any_sync(SPHRT_FULL, tb < SPHRT_INF)) {           // cones crossed twice inside the chord
+                int geo;
+                if (tb < SPHRT_INF) rb = cone_region_ne(T.ne, c, i, tb, &geo);
+            }
+            const bool a_down = ta < R.t_turn;                      // first crossing (towards the turn)
+            const bool a_up = ta < SPHRT_INF && !a_down;
+            const bool b_up = tb < SPHRT_INF;
+            if (a_up && b_up) bad = true;                           // two crossings after the turn
+            const uint32_t md = __ballot_sync(SPHRT_FULL, a_down);
+            const uint32_t mu = __ballot_sync(SPHRT_FULL, a_up || b_up);
+            if (a_down) {
+                const int slot = e_mid - 1 - (nDown + __popc(md & lt_mask));
+                if (slot >= 0) {
+                    sts_f64(tEbuf + 8u * slot, ta);
+                    sts_s32(rEbuf + 4u * slot, ra >= 0 ? ra * na : (ra == -2 ? kUnchangedState : kInvalidState));
+                } else bad = true;
+                unchanged |= ra == -2;
+            }
+            if (a_up || b_up) {
+                const int slot = e_mid + nUp + __popc(mu & lt_mask);
+                const int rr = a_up ? ra : rb;
+                if (slot < P.capE) {
+                    sts_f64(tEbuf + 8u * slot, a_up ? ta : tb);
+                    sts_s32(rEbuf + 4u * slot, rr >= 0 ? rr * na : (rr == -2 ? kUnchangedState : kInvalidState));
+                } else bad = true;
+                unchanged |= rr == -2;
+            }
+            nDown += __popc(md); nUp += __popc(mu);
         }
-        if (__any_sync(SPHRT_FULL, tb < SPHRT_INF)) {           // cones crossed twice inside the chord
-            int geo;
-            if (tb < SPHRT_INF) rb = cone_region_ne(T.ne, c, i, tb, &geo);
-        }
-        const bool a_down = ta < R.t_turn;                      // first crossing (towards the turn)
-        const bool a_up = ta < SPHRT_INF && !a_down;
-        const bool b_up = tb < SPHRT_INF;
-        if (a_up && b_up) bad = true;                           // two crossings after the turn
-        const uint32_t md = __ballot_sync(SPHRT_FULL, a_down);
-        const uint32_t mu = __ballot_sync(SPHRT_FULL, a_up || b_up);
-        if (a_down) {
-            const int slot = e_mid - 1 - (nDown + __popc(md & lt_mask));
-            if (slot >= 0) {
-                sts_f64(tEbuf + 8u * slot, ta);
-                sts_s32(rEbuf + 4u * slot, ra >= 0 ? ra * na : (ra == -2 ? kUnchangedState : kInvalidState));
-            } else bad = true;
-            unchanged |= ra == -2;
-        }
-        if (a_up || b_up) {
-            const int slot = e_mid + nUp + __popc(mu & lt_mask);
-            const int rr = a_up ? ra : rb;
-            if (slot < P.capE) {
-                sts_f64(tEbuf + 8u * slot, a_up ? ta : tb);
-                sts_s32(rEbuf + 4u * slot, rr >= 0 ? rr * na : (rr == -2 ? kUnchangedState : kInvalidState));
-            } else bad = true;
-            unchanged |= rr == -2;
-        }
-        nDown += __popc(md); nUp += __popc(mu);
     }
     if (__any_sync(SPHRT_FULL, bad)) return -1;           // (also keeps the offsets below in range)
     const uint32_t tE = tEbuf + 8u * (e_mid - nDown), rE = rEbuf + 4u * (e_mid - nDown);
@@ -232,43 +267,50 @@ __device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, 
     const uint32_t tA = wbase + P.off_tA, rA = wbase + P.off_rA + 4u;
     const int a_count = R.a_cd < 0 ? -R.a_cd : R.a_cd, a_dir = R.a_cd < 0 ? -1 : 1;
     int nA = 0;
-    for (int k0 = 0; k0 < a_count; k0 += 32) {
-        const int k = k0 + lane;
-        double t = SPHRT_INF;
-        int geo = 0;
-        if (k < a_count) {
-            int pl = R.a_first + k * a_dir;                    // seam: plane na going up, 0 going down
-            if (pl > na) pl -= na;
-            if (pl < 0) pl += na;
-            if (pl == 0 || pl == na) {
-                // the seam: one half-plane the reference evaluates twice, earlier root wins
-                FastAzimuth::eval(g, c, pl, t_in, false, t, geo);
-                if (!(t <= t_out)) t = SPHRT_INF;
-            } else {
-                // plane_event() with the validity kept in a predicate.  Two exact identities are
-                // used: fma(0, z, y) == y for finite z (the reference's einsum carries the zero
-                // z-component of the plane normal, :508-513), and cross == den bit for bit
-                // ((-sa) * d0 == -(sa * d0))
-                const double ca = lds_f64(T.cos_a + 8u * pl), sa = lds_f64(T.sin_a + 8u * pl);
-                const double num = fma_rn(ca, c.x1, (-sa) * c.x0);
-                const double den = fma_rn(ca, c.d1, (-sa) * c.d0);
-                const double tt = -num / den;
-                geo = pl - (den < 0 ? 1 : 0);
-                const double px = tt * c.d0 + c.x0, py = tt * c.d1 + c.x1;
-                const bool valid = !(fabs(den) <= SPHRT_A_PARALLEL) && !(ca * px + sa * py < 0) &&
-                                   tt >= t_in && tt <= t_out;
-                if (valid) t = tt;
+    {
+        int k = lane, pl0 = R.a_first + lane * a_dir;
+        const int pl_step = 32 * a_dir;
+        uint32_t oT = tA, oR = rA;
+#pragma unroll 1
+        for (; __any_sync(SPHRT_FULL, k < a_count); k += 32, pl0 += pl_step) {
+            double t = SPHRT_INF;
+            int geo = 0;
+            if (k < a_count) {
+                int pl = pl0;                                      // seam: plane na going up, 0 going down
+                if (pl > na) pl -= na;
+                if (pl < 0) pl += na;
+                if (pl == 0 || pl == na) {
+                    warp_seam_plane(T, c, pl, t_in, t, geo);
+                    if (!(t <= t_out)) t = SPHRT_INF;
+                } else {
+                    // plane_event() with the validity kept in a predicate.  Two exact identities
+                    // are used: fma(0, z, y) == y for finite z (the reference's einsum carries the
+                    // zero z-component of the plane normal, :508-513), and cross == den bit for bit
+                    // ((-sa) * d0 == -(sa * d0))
+                    double ca, sa;
+                    lds_f64x2(T.plane + 16u * pl, ca, sa);
+                    const double num = fma_rn(ca, c.x1, (-sa) * c.x0);
+                    const double den = fma_rn(ca, c.d1, (-sa) * c.d0);
+                    const double tt = -num / den;
+                    geo = pl - (den < 0 ? 1 : 0);
+                    const double px = tt * c.d0 + c.x0, py = tt * c.d1 + c.x1;
+                    const bool valid = !(fabs(den) <= SPHRT_A_PARALLEL) && !(ca * px + sa * py < 0) &&
+                                       tt >= t_in && tt <= t_out;
+                    if (valid) t = tt;
+                }
+                if (k == a_count - 1 && t < SPHRT_INF) bad = true;     // guard
             }
-            if (k == a_count - 1 && t < SPHRT_INF) bad = true;     // guard
+            const bool hit = t < SPHRT_INF;
+            const uint32_t mv = __ballot_sync(SPHRT_FULL, hit);
+            if (hit) {
+                const int slot = __popc(mv & lt_mask);
+                const int reg = geo < 0 ? geo + na : (geo >= na ? geo - na : geo);   // full circle
+                sts_f64(oT + 8u * slot, t);
+                sts_s32(oR + 4u * slot, reg);
+            }
+            const int cnt = __popc(mv);
+            nA += cnt; oT += 8u * cnt; oR += 4u * cnt;
         }
-        const uint32_t mv = __ballot_sync(SPHRT_FULL, t < SPHRT_INF);
-        if (t < SPHRT_INF) {
-            const int slot = nA + __popc(mv & lt_mask);
-            const int reg = FastAzimuth::to_region(g, geo);
-            sts_f64(tA + 8u * slot, t);
-            sts_s32(rA + 4u * slot, reg >= 0 ? reg : kInvalidState);
-        }
-        nA += __popc(mv);
     }
     if (lane == 0) {
         sts_f64(tA + 8u * nA, SPHRT_INF);
@@ -348,16 +390,17 @@ __device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, 
     const int nR = 2 * m;
     {
         const double tang = 1e-17 * (1.0 + c.nx2);
-        for (int k = lane; k < m; k += 32) {           // both roots share the square root
-            const double r = lds_f64(T.r_b + 8u * (T.nr - k));
-            const double r2 = r * r;
+        uint32_t src = T.r2 + 8u * (T.nr - lane), lo = tR + 8u * lane, hi = tR + 8u * (nR - 1 - lane);
+#pragma unroll 1
+        for (int k = lane; k < m; k += 32, src -= 256u, lo += 256u, hi -= 256u) {   // both roots share the square root
+            const double r2 = lds_f64(src);
             const double arg = r2 - c.dperp2;
             const double t1c = sqrt(arg);
             // inward roots enter shell i - 1, outward roots shell i; when tangent within rounding
             // the reference decides from the sign of d.p: bail out
             if (!(arg >= tang + 1e-17 * r2)) bad = true;
-            sts_f64(tR + 8u * k, c.tc - t1c);
-            sts_f64(tR + 8u * (nR - 1 - k), c.tc + t1c);
+            sts_f64(lo, c.tc - t1c);
+            sts_f64(hi, c.tc + t1c);
         }
         for (int k = lane; k < P.padR; k += 32) sts_f64(tR + 8u * (nR + k), SPHRT_INF);
     }
@@ -408,12 +451,28 @@ __device__ __forceinline__ int warp_walk_ray(const GridView& g, const Tab32& T, 
             t = tn;                                                                               \
         }
         int q = 0;
-        for (; q + 2 <= c2; q += 2) {
-            SPHRT_WARP_STEP(0, 0)
-            SPHRT_WARP_STEP(1, 1)
-            cE += 16u; cS += 8u;
+        if constexpr (kWarpDepth == 4) {
+            for (; q + 4 <= c2; q += 4) {
+                SPHRT_WARP_STEP(0, 0)
+                SPHRT_WARP_STEP(1, 1)
+                SPHRT_WARP_STEP(2, 2)
+                SPHRT_WARP_STEP(3, 3)
+                cE += 32u; cS += 16u;
+            }
+            if (q + 2 <= c2) {
+                SPHRT_WARP_STEP(0, 0)
+                SPHRT_WARP_STEP(1, 1)
+                cE += 16u; cS += 8u; q += 2;
+            }
+            if (q < c2) SPHRT_WARP_STEP(2, 0)
+        } else {
+            for (; q + 2 <= c2; q += 2) {
+                SPHRT_WARP_STEP(0, 0)
+                SPHRT_WARP_STEP(1, 1)
+                cE += 16u; cS += 8u;
+            }
+            if (q < c2) SPHRT_WARP_STEP(0, 0)
         }
-        if (q < c2) SPHRT_WARP_STEP(0, 0)
 #undef SPHRT_WARP_STEP
     }
     return n;

@@ -5,21 +5,39 @@ usage: ncu_regions.py file.csv [kernel-substring] [segments]"""
 import csv, sys, collections
 path = sys.argv[1]; want = sys.argv[2] if len(sys.argv) > 2 else ""
 nseg = float(sys.argv[3]) if len(sys.argv) > 3 else 0
-REGIONS = [
-    ("sphrt_warp.cuh", 78, 94, "co-rank (both stages)"),
-    ("sphrt_warp.cuh", 95, 121, "per-ray setup"),
-    ("sphrt_warp.cuh", 122, 184, "elevation candidates (list build)"),
-    ("sphrt_warp.cuh", 185, 240, "azimuth candidates (list build)"),
-    ("sphrt_warp.cuh", 241, 275, "stage 1: merge E+A"),
-    ("sphrt_warp.cuh", 276, 299, "radial list"),
-    ("sphrt_warp.cuh", 300, 360, "stage 2: merge R+EA, segments"),
-    ("sphrt_walker.cuh", 154, 215, "cone primitives (quadratic, roots, region, shadow)"),
-    ("sphrt_walker.cuh", 216, 237, "plane_event (seam)"),
+import os
+HERE = os.path.dirname(os.path.abspath(__file__))
+WARP = os.path.join(HERE, "..", "sph_raytracer_b200", "csrc", "sphrt_warp.cuh")
+
+
+def warp_regions():
+    """Line ranges of the phases of warp_walk_ray, found by their marker comments."""
+    marks = [("__device__ __forceinline__ int warp_corank", "co-rank (both stages)"),
+             ("__device__ __forceinline__ int warp_walk_ray", "per-ray setup"),
+             ("// ---- elevation:", "elevation candidates (list build)"),
+             ("// ---- azimuth:", "azimuth candidates (list build)"),
+             ("// ---- stage 1:", "stage 1: merge E+A"),
+             ("// ---- radial list", "radial list"),
+             ("// ---- stage 2:", "stage 2: merge R+EA, segments"),
+             ("}  // namespace sphrt", None)]
+    lines = open(WARP).read().split("\n")
+    pos = []
+    for text, name in marks:
+        for k, l in enumerate(lines):
+            if text in l:
+                pos.append((k + 1, name)); break
+    return [("sphrt_warp.cuh", pos[k][0], pos[k + 1][0] - 1, pos[k][1]) for k in range(len(pos) - 1)]
+
+
+REGIONS = warp_regions() + [
+    ("sphrt_warp.cuh", 0, 100000, "shared-memory helpers (ld/st.shared asm)"),
+    ("sphrt_walker.cuh", 154, 230, "cone primitives (quadratic, roots, region, shadow)"),
+    ("sphrt_walker.cuh", 231, 255, "plane_event (seam)"),
     ("sphrt_walker.cuh", 60, 90, "fma/dot/norm helpers"),
     ("sphrt_fast.cuh", 0, 400, "FastAzimuth helpers"),
-    ("sphrt_kernels.cuh", 120, 330, "sink (gather / RED, reduction, store)"),
+    ("sphrt_kernels.cuh", 120, 420, "sink (gather / RED, reduction, store)"),
     ("sphrt_kernels.cuh", 80, 112, "stage_tables"),
-    ("sphrt_kernels.cuh", 820, 900, "kernel loop (hand-out, record load)"),
+    ("sphrt_kernels.cuh", 421, 100000, "kernel loop (hand-out, record load)"),
 ]
 rows = list(csv.reader(open(path)))
 cur_file = cur_fn = None; hdr = None
