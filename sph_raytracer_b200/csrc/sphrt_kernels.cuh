@@ -902,17 +902,23 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
     const Tab32 T(tab32, kg.nr, kg.ne, kg.na);
     const unsigned n_recs = *n_recs_p;
     unsigned n_ok = 0, n_fail = 0;
-    for (;;) {
-        unsigned b = 0;
-        if (lane == 0) b = atomicAdd(counter, kWarpBatch);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_recs) break;
-        const unsigned e = b + kWarpBatch < n_recs ? b + kWarpBatch : n_recs;
-        // the records of the batch into L1 (80 bytes each, contiguous)
-        if (lane < 6) {
-            const char* p = reinterpret_cast<const char*>(recs + b) + 128 * lane;
+    // batches are handed out one ahead: the atomic and the record prefetch of the next batch are
+    // in flight while the current one is walked
+    auto grab = [&]() {
+        unsigned v = 0;
+        if (lane == 0) v = atomicAdd(counter, kWarpBatch);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (v < n_recs && lane < 6) {
+            const unsigned e = v + kWarpBatch < n_recs ? v + kWarpBatch : n_recs;
+            const char* p = reinterpret_cast<const char*>(recs + v) + 128 * lane;
             if (p < reinterpret_cast<const char*>(recs + e)) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
         }
+        return v;
+    };
+    unsigned b = grab();
+    while (b < n_recs) {
+        const unsigned e = b + kWarpBatch < n_recs ? b + kWarpBatch : n_recs;
+        const unsigned b_next = grab();
         for (unsigned k = b; k < e; k++) {
             const PlanRec R = load_plan_rec(recs + k);
             const int64_t ray = ray_base + R.ray;
@@ -929,6 +935,7 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
             }
             __syncwarp();              // the lists are reused by the next ray
         }
+        b = b_next;
     }
     if (stats != nullptr && lane == 0) {
         atomicAdd(stats + 0, (unsigned long long)n_ok);

@@ -56,10 +56,14 @@ class CubesModel(_FixedVolume):
     def __init__(self, grid):
         self.grid = grid
         nr, ne, na = grid.shape.r, grid.shape.e, grid.shape.a
-        self.r0, self.r1 = int(nr * .333), int(nr * .666)
-        self.e00, self.e01 = int(ne * .2), int(ne * .3)
-        self.e10, self.e11 = int(ne * .7), int(ne * .9)
-        self.a0, self.a1 = int(na * .4), int(na * .6)
+        # the reference multiplies the axis length by a float32 tensor and truncates
+        # (model.py:58-66); Python float64 products truncate differently for some sizes
+        # (ne = 180: .7 -> 126 in float32, 125 in float64)
+        edges = lambda n, fracs: tuple(int(v) for v in n * torch.tensor(fracs))
+        self.r0, self.r1 = edges(nr, (.333, .666))
+        self.e00, self.e01 = edges(ne, (.2, .3))
+        self.e10, self.e11 = edges(ne, (.7, .9))
+        self.a0, self.a1 = edges(na, (.4, .6))
         self.volume = torch.zeros(grid.shape)
         self.volume[self.r0:self.r1, self.e00:self.e01, self.a0:self.a1] = 1
         self.volume[self.r0:self.r1, self.e10:self.e11, self.a0:self.a1] = 1

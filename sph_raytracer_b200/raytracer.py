@@ -20,7 +20,7 @@ import torch
 from . import _cabi
 from .geometry import ViewGeomCollection
 
-__all__ = ["Operator", "find_starts", "r_torch", "e_torch", "a_torch", "DEVICE", "FTYPE", "ITYPE"]
+__all__ = ["Operator", "find_starts", "find_starts_cuda", "r_torch", "e_torch", "a_torch", "DEVICE", "FTYPE", "ITYPE"]
 
 # module defaults, same names as the reference (raytracer.py:12-15)
 DEVICE = "cuda"
@@ -476,7 +476,28 @@ class Operator:
 
 def find_starts(grid, xs, ftype=FTYPE, device=DEVICE):
     """Voxel index of start points, ``(3, *xs.shape[:-1])`` int64 with -1 = outside
-    (reference raytracer.py:605-644); evaluated by the CUDA extension."""
+    (reference raytracer.py:605-644), on ``device`` like the reference's.
+
+    Evaluated with the same host code the Operator bins its start points with
+    (:func:`_start_cells`: torch's own cart2sph + searchsorted + fix-ups), because a point that
+    sits on a cone or half-plane to the last bit is binned by the last bit of ``atan2``, which
+    differs between torch's CPU library and CUDA's; :func:`find_starts_cuda` is the in-kernel
+    version the walkers use for entry points."""
+    pts = torch.asarray(xs, dtype=torch.float64).cpu()
+    lead = tuple(pts.shape[:-1])
+    r_b = torch.asarray(grid.r_b, dtype=torch.float64).cpu().reshape(-1)
+    e_b = torch.asarray(grid.e_b, dtype=torch.float64).cpu().reshape(-1)
+    a_b = torch.asarray(grid.a_b, dtype=torch.float64).cpu().reshape(-1)
+    cells = _start_cells(r_b, e_b, a_b, pts.reshape(-1, 3).contiguous())
+    out = cells[:, 3:6].to(torch.int64).T.reshape((3,) + lead)
+    dev = torch.device(device)
+    if dev.type == "cuda" and not torch.cuda.is_available():
+        return out
+    return out.to(dev)
+
+
+def find_starts_cuda(grid, xs, device=DEVICE):
+    """:func:`find_starts` evaluated by the CUDA extension (``sphrt_find_starts``: CUDA's atan2)."""
     lib = _cabi.load()
     cdev = _compute_device(device)
     tables = _GridTables(grid, cdev)

@@ -111,6 +111,8 @@ def test_find_starts_known_answers(S):
         shape, x, want = row[:3].astype(int), row[3:6], row[6:9].astype(int)
         got = S.find_starts(S.SphericalGrid(shape=tuple(shape)), x)
         assert got.tolist() == want.tolist()
+        from sph_raytracer_b200.raytracer import find_starts_cuda
+        assert find_starts_cuda(S.SphericalGrid(shape=tuple(shape)), x).tolist() == want.tolist()
 
 
 def _oracle_compare(S, grid, geom, max_seg=None, allow_unstable=0):

@@ -297,3 +297,29 @@ def test_canonical_from_events():
     assert c.tolist() == [1] and v[0, 0].tolist() == [1, 1, 1] and l[0, 0] == 0.75
     c, v, l = canonical_from_events(vox, lens, np.array([-1]), 4)
     assert c.tolist() == [-1]
+
+
+def test_find_starts_runs_on_the_host_and_matches_the_reference_known_answers():
+    """find_starts (reference raytracer.py:605-644) takes the host torch path of _start_cells (the
+    last bit of atan2 decides the bin of a point on a cone / half-plane, and CUDA's differs)."""
+    import sph_raytracer_b200 as S
+    z = np.load(os.path.join(ROOT, "tests", "golden", "known_answers.npz"))
+    for row in z["find_starts"]:
+        shape, x, want = row[:3].astype(int), row[3:6], row[6:9].astype(int)
+        got = S.find_starts(S.SphericalGrid(shape=tuple(shape)), torch.from_numpy(x), device="cpu")
+        assert got.dtype == torch.int64 and got.tolist() == want.tolist()
+    # batched points keep their leading shape, like the reference
+    pts = torch.randn(4, 5, 3, dtype=torch.float64)
+    out = S.find_starts(S.SphericalGrid(shape=(6, 7, 8)), pts, device="cpu")
+    assert tuple(out.shape) == (3, 4, 5)
+
+
+def test_cubes_model_boxes_equal_the_reference_float32_arithmetic():
+    """CubesModel box edges: the reference truncates n * float32 fraction (model.py:58-66); on the
+    config-5 grid (ne = 180) float64 arithmetic would give 125 instead of 126."""
+    import sph_raytracer_b200 as S
+    from sph_raytracer_b200.model import CubesModel
+    m = CubesModel(S.SphericalGrid(shape=(200, 180, 360)))
+    assert (m.r0, m.r1, m.e00, m.e01, m.e10, m.e11, m.a0, m.a1) == (66, 133, 36, 54, 126, 162, 144, 216)
+    m = CubesModel(S.SphericalGrid(shape=(90, 170, 330)))
+    assert (m.e10, m.e11, m.a0, m.a1) == (119, 153, 132, 198)
