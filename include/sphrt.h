@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 3
+#define SPHRT_VERSION 4
 
 enum {
     SPHRT_OK = 0,
@@ -178,6 +178,9 @@ int sphrt_find_starts(const sphrt_grid *grid, int64_t n, const double *xs, int32
 int sphrt_version(void);
 const char *sphrt_error_string(int code);
 int sphrt_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (every entry point
+ * counts its own launches; benchmarks report the difference over their timed region). */
+unsigned long long sphrt_launch_count(void);
 
 #ifdef __cplusplus
 }

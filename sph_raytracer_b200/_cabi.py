@@ -15,7 +15,8 @@ F32, F64 = 0, 1
 EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphrt_scratch_bytes",
            "sphrt_forward", "sphrt_adjoint", "sphrt_count_segments", "sphrt_trace_segments",
            "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind",
-           "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates")
+           "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates",
+           "sphrt_launch_count")
 
 
 class Grid(ctypes.Structure):
@@ -56,6 +57,8 @@ def load(path=None):
     lib.sphrt_error_string.restype = ctypes.c_char_p
     lib.sphrt_error_string.argtypes = [c_int]
     lib.sphrt_last_cuda_error.restype = c_int
+    lib.sphrt_launch_count.restype = ctypes.c_ulonglong
+    lib.sphrt_launch_count.argtypes = []
     lib.sphrt_scratch_bytes.restype = c_int64
     lib.sphrt_scratch_bytes.argtypes = [P(Grid), c_int64]
     vol_args = [P(Grid), P(Rays), c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]

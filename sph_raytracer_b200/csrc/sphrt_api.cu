@@ -3,6 +3,7 @@
 #include "sphrt_kernels.cuh"
 
 int sphrt_g_last_cuda_error = 0;
+unsigned long long sphrt_g_launches = 0;
 
 // ---- C ABI --------------------------------------------------------------------------------------
 
@@ -11,6 +12,8 @@ extern "C" {
 int sphrt_version(void) { return SPHRT_VERSION; }
 
 int sphrt_last_cuda_error(void) { return sphrt_g_last_cuda_error; }
+
+unsigned long long sphrt_launch_count(void) { return sphrt_g_launches; }
 
 const char* sphrt_error_string(int code)
 {

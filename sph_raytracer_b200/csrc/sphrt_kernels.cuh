@@ -50,6 +50,7 @@ constexpr int kQueueBytes = 3 * kQueue * kBlock * (int)(sizeof(double) + sizeof(
 // one slot for the whole library (defined in sphrt_api.cu): the last cudaError_t a launch returned
 }  // namespace
 extern int sphrt_g_last_cuda_error;
+extern unsigned long long sphrt_g_launches;      // kernels this library has launched (sphrt_launch_count)
 namespace {
 
 struct KRays {
@@ -1218,8 +1219,9 @@ int check_rays(const sphrt_rays* r)
     return SPHRT_OK;
 }
 
-int cuda_status()
+int cuda_status()          // called once after every kernel launch
 {
+    sphrt_g_launches++;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { sphrt_g_last_cuda_error = (int)e; return SPHRT_ECUDA; }
     return SPHRT_OK;

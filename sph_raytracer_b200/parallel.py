@@ -13,9 +13,10 @@ is exercised with ``gloo`` in the CPU tests).
 import torch
 import torch.distributed as dist
 
-from .geometry import ViewGeomCollection
+from .geometry import ViewGeom, ViewGeomCollection
 
-__all__ = ["shard_bounds", "shard_collection", "ShardedOperator", "allreduce_gradient"]
+__all__ = ["shard_bounds", "shard_collection", "shard_detector_rows", "ShardedOperator",
+           "allreduce_gradient"]
 
 
 def shard_bounds(n_items, rank, world):
@@ -33,6 +34,41 @@ def shard_collection(geoms, rank, world):
     if hi == lo:
         raise ValueError(f"rank {rank} of {world} would own no observation ({len(geoms)} in total)")
     return ViewGeomCollection(*geoms.geoms[lo:hi]), (lo, hi)
+
+
+def shard_detector_rows(geoms, rank, world):
+    """Fewer observations than ranks (a single vantage, ``examples/single_vantage.py``): the
+    detector ROWS of all observations, taken together, are sharded instead.
+
+    ``geoms`` is one geometry or a collection; every observation contributes ``shape[-2]`` rows of
+    ``shape[-1]`` pixels.  Returns a plain :class:`ViewGeom` with this rank's rows (explicit start
+    and direction per pixel, shape ``(rows, W)``) and the block ``(lo, hi)`` of the flattened
+    (observation, row) axis it covers, so that the ranks' results concatenate to the full
+    ``(n_obs * H, W)`` stack."""
+    obs = list(geoms.geoms) if isinstance(geoms, ViewGeomCollection) else [geoms]
+    rays = [torch.asarray(g.rays, dtype=torch.float64) for g in obs]
+    if any(r.dim() != 3 for r in rays):
+        raise ValueError("detector-row sharding needs (H, W) detectors")
+    heights = [r.shape[0] for r in rays]
+    lo, hi = shard_bounds(sum(heights), rank, world)
+    if hi == lo:
+        raise ValueError(f"rank {rank} of {world} would own no detector row ({sum(heights)} in total)")
+    parts_d, parts_x, first = [], [], 0
+    for g, r, h in zip(obs, rays, heights):
+        a, b = max(lo, first), min(hi, first + h)
+        if a < b:
+            d = r[a - first:b - first]
+            x = torch.asarray(g.ray_starts, dtype=torch.float64).broadcast_to(r.shape)[a - first:b - first]
+            parts_d.append(d); parts_x.append(x)
+        first += h
+    # (not through ViewGeom.__init__: it normalises the directions once more, and a direction that
+    # differs in the last bit is a different ray -- the shards must trace exactly the rays of the
+    # unsharded geometry)
+    geom = ViewGeom.__new__(ViewGeom)
+    geom.ray_starts = torch.cat(parts_x).contiguous()
+    geom.rays = torch.cat(parts_d).contiguous()
+    geom.shape = geom.rays.shape[:-1]
+    return geom, (lo, hi)
 
 
 def allreduce_gradient(grad, group=None):
@@ -93,8 +129,15 @@ class ShardedOperator:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank, self.world, self.group = rank, world, group
         self.grid = grid
-        self.geom, (self.lo, self.hi) = shard_collection(geoms, rank, world)
         self.dynamic = bool(getattr(grid, "dynamic", False))
+        n_obs = len(geoms.geoms) if isinstance(geoms, ViewGeomCollection) else 1
+        self.by_rows = n_obs < world and not self.dynamic
+        if self.by_rows:
+            # fewer observations than ranks: shard the detector rows (results are (rows, W) blocks
+            # of the flattened (observation, row) axis)
+            self.geom, (self.lo, self.hi) = shard_detector_rows(geoms, rank, world)
+        else:
+            self.geom, (self.lo, self.hi) = shard_collection(geoms, rank, world)
         local_grid = grid
         if self.dynamic:
             # the time axis is sharded with the observations: a grid with this rank's slices

@@ -27,7 +27,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib = _cabi.load()
-    assert lib.sphrt_version() == 3
+    assert lib.sphrt_version() == 4
     assert lib.sphrt_error_string(-3).decode().startswith("scratch")
     # argument validation happens before any CUDA call
     g = _cabi.Grid(0, 1, 1, 0, *([0] * 7))
@@ -323,3 +323,73 @@ def test_cubes_model_boxes_equal_the_reference_float32_arithmetic():
     assert (m.r0, m.r1, m.e00, m.e01, m.e10, m.e11, m.a0, m.a1) == (66, 133, 36, 54, 126, 162, 144, 216)
     m = CubesModel(S.SphericalGrid(shape=(90, 170, 330)))
     assert (m.e10, m.e11, m.a0, m.a1) == (119, 153, 132, 198)
+
+
+# ---- fewer observations than ranks: detector rows are sharded ------------
+def test_shard_detector_rows_covers_every_row_once():
+    g1 = S.ConeRectGeom((5, 4), (5.0, 0.0, 0.0), fov=(45, 45))
+    g2 = S.ConeRectGeom((3, 4), (0.0, 5.0, 1.0), fov=(30, 30))
+    coll = S.ViewGeomCollection.__new__(S.ViewGeomCollection)       # ragged heights: a bare list
+    coll.geoms = [g1, g2]
+    want_d = torch.cat([g1.rays, g2.rays])
+    want_x = torch.cat([g1.ray_starts.broadcast_to(g1.rays.shape), g2.ray_starts.broadcast_to(g2.rays.shape)])
+    for world in (1, 2, 3, 8):
+        got_d, got_x, blocks = [], [], []
+        for rank in range(world):
+            geom, (lo, hi) = P.shard_detector_rows(coll, rank, world)
+            assert tuple(geom.rays.shape) == (hi - lo, 4, 3) == tuple(geom.ray_starts.shape)
+            got_d.append(geom.rays); got_x.append(geom.ray_starts); blocks.append((lo, hi))
+        assert blocks[0][0] == 0 and blocks[-1][1] == 8
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert torch.equal(torch.cat(got_d), want_d) and torch.equal(torch.cat(got_x), want_x)
+    with pytest.raises(ValueError):
+        P.shard_detector_rows(g2, 3, 4)                              # 3 rows, 4 ranks: rank 3 owns nothing
+
+
+class _RowOp:
+    """CPU stand-in: y[row, pixel] = <direction of the pixel, fixed vector> * sum(x) -- enough to see
+    that every rank traces its own rows and that the gradient is all-reduced."""
+
+    def __init__(self, grid, geom, **kw):
+        self.grid, self.geom, self.device = grid, geom, "cpu"
+        self.w = (torch.asarray(geom.rays) * torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)).sum(-1)
+
+    def __call__(self, density):
+        return self.w * density.sum()
+
+    def T(self, y):
+        return torch.full(tuple(self.grid.shape), float((self.w * y).sum()), dtype=torch.float64)
+
+
+def _row_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = S.SphericalGrid((2, 3, 4))
+    geom = S.ConeRectGeom((6, 5), (5.0, 0.0, 0.0), fov=(45, 45))      # ONE observation, two ranks
+    sop = P.ShardedOperator(grid, geom, _RowOp)
+    x = torch.ones(2, 3, 4, dtype=torch.float64, requires_grad=True)
+    y = sop(x)
+    y.sum().backward()
+    q.put((rank, sop.by_rows, sop.lo, sop.hi, y.detach().numpy(), x.grad.numpy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_operator_shards_detector_rows_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_row_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    geom = S.ConeRectGeom((6, 5), (5.0, 0.0, 0.0), fov=(45, 45))
+    w = (geom.rays * torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)).sum(-1)
+    assert [(r[1], r[2], r[3]) for r in res] == [(True, 0, 3), (True, 3, 6)]
+    for rank, by_rows, lo, hi, y, gx in res:
+        assert np.allclose(y, (w[lo:hi] * 24).numpy())
+        assert np.allclose(gx, float(w.sum()))                      # global gradient on every rank
