@@ -323,7 +323,9 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     dynamic = grid.dynamic
     geom, local_grid, (lo, hi), sharding = _shard(grid, geoms, rank, world)
     torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats(dev)
+    mem_base = torch.cuda.memory_allocated(dev)        # buffers of the harness itself (L2 flush, ...)
     t0 = time.perf_counter()
     op = S.Operator(local_grid, geom, device=dev)
     torch.cuda.synchronize(dev)
@@ -407,7 +409,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
             step_e2e()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
-    peak_bytes = torch.cuda.max_memory_allocated(dev)
+    peak_bytes = torch.cuda.max_memory_allocated(dev) - mem_base
     clocks = sampler.summary() if sampler is not None else None
 
     stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build], dtype=torch.float64, device=dev)
