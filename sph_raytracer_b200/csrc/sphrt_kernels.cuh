@@ -642,8 +642,10 @@ __device__ __forceinline__ void for_each_flagged(const uint32_t* mask, int64_t n
 template <class Op>
 __global__ void __launch_bounds__(kBlock, SPHRT_TRACKED_MIN_BLOCKS)
 walk_tracked_masked_kernel(sphrt_grid kg, KRays kr, Op op, int table_doubles_smem,
-                           const uint32_t* mask, int64_t n_words, unsigned long long* chunk_counter)
+                           const uint32_t* mask, int64_t n_words, unsigned long long* chunk_counter,
+                           const unsigned* n_work /* may be null: number of flagged rays, 0 = nothing to do */)
 {
+    if (n_work != nullptr && *n_work == 0) return;
     extern __shared__ double sm_tables[];
     __shared__ int64_t flag_queue[(kBlock / 32) * kFlagQueue];
     const GridView g = stage_tables(kg, sm_tables);
@@ -810,7 +812,8 @@ constexpr int kPlanBlock = 256;
 
 __global__ void __launch_bounds__(kPlanBlock)
 plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, PlanRec* recs,
-                 unsigned* n_recs, uint32_t* mask_listed, uint32_t* mask_tracked, int32_t* miss_count,
+                 unsigned* n_recs /* [0] ordinary rays, from the front; [1] all-cones rays, from the back */,
+                 int64_t cap, uint32_t* mask_listed, uint32_t* mask_tracked, int32_t* miss_count,
                  unsigned long long* stats)
 {
     extern __shared__ double sm_tables[];
@@ -831,23 +834,30 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
         start_index = i / kr.rps;
         ray_setup(c, x, d);
         CoopStartCache cache{-1, true, true, 0, 0, 0};
-        cls = coop_plan_ray<COOP_ORDINARY>(g, c, x, P, start_index, kr.cells, cache, rec);
-        if (!table_ok && cls == COOP_RAY) cls = COOP_TRACKED;
+        cls = coop_plan_ray<COOP_BOTH>(g, c, x, P, start_index, kr.cells, cache, rec);
+        if (!table_ok && cls == COOP_RAY) cls = rec.e_mid == 0 ? COOP_LISTED : COOP_TRACKED;
         if (cls == COOP_MISS && miss_count != nullptr) miss_count[i] = 0;
     }
-    const uint32_t m_ray = __ballot_sync(0xffffffffu, cls == COOP_RAY);
+    const bool allc = cls == COOP_RAY && rec.e_mid == 0;           // walked in all-cones mode
+    const uint32_t m_ray = __ballot_sync(0xffffffffu, cls == COOP_RAY && !allc);
+    const uint32_t m_all = __ballot_sync(0xffffffffu, allc);
     const uint32_t m_listed = __ballot_sync(0xffffffffu, cls == COOP_LISTED);
     const uint32_t m_tracked = __ballot_sync(0xffffffffu, cls == COOP_TRACKED);
-    unsigned slot0 = 0;
+    unsigned slot0 = 0, slot1 = 0;
     if (lane == 0 && li < n) {
         mask_listed[i >> 5] = m_listed;
         mask_tracked[i >> 5] = m_tracked;
         if (m_ray) slot0 = atomicAdd(n_recs, (unsigned)__popc(m_ray));
+        if (m_all) slot1 = atomicAdd(n_recs + 1, (unsigned)__popc(m_all));
+        if (m_listed) atomicAdd(n_recs + 4, (unsigned)__popc(m_listed));      // work of the fallback passes
+        if (m_tracked) atomicAdd(n_recs + 5, (unsigned)__popc(m_tracked));
         if (stats != nullptr) {
+            if (m_listed) atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));
             if (m_tracked) atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
         }
     }
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    slot1 = __shfl_sync(0xffffffffu, slot1, 0);
     if (cls == COOP_RAY) {
         PlanRec r;
         r.d0 = rec.d0; r.d1 = rec.d1; r.d2 = rec.d2;
@@ -857,7 +867,9 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
         r.e_first = (int16_t)rec.e_first; r.e_cs = (int16_t)(rec.e_count * rec.e_step);
         r.a_first = (int16_t)rec.a_first; r.a_cd = (int16_t)(rec.a_count * rec.a_dir);
         r.se0 = (int16_t)rec.se0; r.sa0 = (int16_t)rec.sa0;
-        store_plan_rec(recs + slot0 + __popc(m_ray & ((1u << lane) - 1u)), r);
+        const uint32_t lt = (1u << lane) - 1u;
+        if (allc) store_plan_rec(recs + (cap - 1 - (int64_t)(slot1 + __popc(m_all & lt))), r);
+        else store_plan_rec(recs + slot0 + __popc(m_ray & lt), r);
     }
 }
 
@@ -868,11 +880,13 @@ constexpr int kWarpMaxWarps = SPHRT_WARP_WARPS;
 constexpr unsigned kWarpBatch = 8;              // records per hand-out
 
 // walk_warp_kernel: persistent warps take batches of planned rays from the dense record list.
-template <class Op>
+// kAllCones: the list of all-cones records (stored from the back of the buffer: `recs` points at its
+// first record and is walked downwards); failures go to pass B's mask.
+template <class Op, bool kAllCones>
 __global__ void __launch_bounds__(kWarpMaxWarps * 32, 1)
 walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPlan P,
                  const PlanRec* __restrict__ recs, const unsigned* n_recs_p, int64_t ray_base,
-                 uint32_t* mask_tracked, unsigned* counter, unsigned long long* stats)
+                 uint32_t* mask_back, unsigned* counter, unsigned* n_back, unsigned long long* stats)
 {
     extern __shared__ __align__(16) double sm_tables[];
     // derived tables (Tab32): r_b^2 | { cos^2 e_b, shadow sign } | { cos a_b, sin a_b }
@@ -902,7 +916,9 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
     const uint32_t lt_mask = __shfl_sync(0xffffffffu, (1u << lane) - 1u, lane);
     const Tab32 T(tab32, kg.nr, kg.ne, kg.na);
     const unsigned n_recs = *n_recs_p;
+    if (n_recs == 0) return;
     unsigned n_ok = 0, n_fail = 0;
+    auto rec_at = [&](unsigned k) { return kAllCones ? recs - k : recs + k; };
     // batches are handed out one ahead: the atomic and the record prefetch of the next batch are
     // in flight while the current one is walked
     auto grab = [&]() {
@@ -911,8 +927,9 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
         v = __shfl_sync(0xffffffffu, v, 0);
         if (v < n_recs && lane < 6) {
             const unsigned e = v + kWarpBatch < n_recs ? v + kWarpBatch : n_recs;
-            const char* p = reinterpret_cast<const char*>(recs + v) + 128 * lane;
-            if (p < reinterpret_cast<const char*>(recs + e)) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+            const PlanRec* first = kAllCones ? rec_at(e - 1) : rec_at(v);       // lowest address of the batch
+            const char* p = reinterpret_cast<const char*>(first) + 128 * lane;
+            if (p < reinterpret_cast<const char*>(first + (e - v))) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
         }
         return v;
     };
@@ -921,14 +938,15 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
         const unsigned e = b + kWarpBatch < n_recs ? b + kWarpBatch : n_recs;
         const unsigned b_next = grab();
         for (unsigned k = b; k < e; k++) {
-            const PlanRec R = load_plan_rec(recs + k);
+            const PlanRec R = load_plan_rec(rec_at(k));
             const int64_t ray = ray_base + R.ray;
             if (op.void_ray(ray)) continue;
             typename Op::WSink sink = op.wbegin(ray);
-            const int nev = warp_walk_ray<Op::kEvents>(T, P, wbase, R, starts + 3 * (int64_t)R.start, lane, lt_mask, sink);
+            const int nev = warp_walk_ray<Op::kEvents, kAllCones>(T, P, wbase, R, starts + 3 * (int64_t)R.start, lane, lt_mask, sink);
             if (nev < 0) {
-                // a structural check failed: the per-thread walker takes the ray
-                if (lane == 0) atomicOr(mask_tracked + (ray >> 5), 1u << (ray & 31));
+                // a structural check failed: a per-thread walker takes the ray (sorted-list walker
+                // of pass B for the all-cones rays)
+                if (lane == 0) { atomicOr(mask_back + (ray >> 5), 1u << (ray & 31)); atomicAdd(n_back, 1u); }
                 n_fail++;
             } else {
                 op.wend(ray, sink, lane, nev);
@@ -940,7 +958,7 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
     }
     if (stats != nullptr && lane == 0) {
         atomicAdd(stats + 0, (unsigned long long)n_ok);
-        atomicAdd(stats + 2, (unsigned long long)n_fail);
+        atomicAdd(stats + (kAllCones ? 1 : 2), (unsigned long long)n_fail);
         atomicAdd(stats + 3, (unsigned long long)n_fail);
     }
 }
@@ -953,8 +971,9 @@ template <class Op>
 __global__ void __launch_bounds__(kListBlock)
 walk_listed_kernel(sphrt_grid kg, KRays kr, Op op, const uint32_t* listed_mask, int64_t n_words,
                    int table_doubles_smem, double* glist_t, int* glist_r,
-                   unsigned long long* chunk_counter)
+                   unsigned long long* chunk_counter, const unsigned* n_work)
 {
+    if (n_work != nullptr && *n_work == 0) return;
     extern __shared__ double sm_tables[];
     __shared__ int64_t flag_queue[(kListBlock / 32) * kFlagQueue];
     const GridView g = stage_tables(kg, sm_tables);
@@ -1241,7 +1260,7 @@ int64_t scratch_bytes_before_recs(const sphrt_grid* grid, int64_t n_rays)
 template <class Op>
 int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const uint32_t* mask,
                   void* lists, size_t smem, const ListPlan& lp, unsigned long long* chunk_counter,
-                  cudaStream_t st)
+                  cudaStream_t st, const unsigned* n_work = nullptr)
 {
     double* glist_t = nullptr;
     int* glist_r = nullptr;
@@ -1253,7 +1272,7 @@ int launch_listed(const sphrt_grid* grid, const KRays& kr, const Op& op, const u
         cudaFuncSetAttribute(walk_listed_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lp.smem);
     walk_listed_kernel<Op><<<(unsigned)lp.blocks, lp.threads, lp.smem, st>>>(
         *grid, kr, op, mask, (kr.n + 31) / 32, (int)(smem / sizeof(double)), glist_t, glist_r,
-        chunk_counter);
+        chunk_counter, n_work);
     return cuda_status();
 }
 
@@ -1283,7 +1302,10 @@ int launch_coop(const PassContext& cx, const CoopLaunch& cl, const Op& op, const
 }
 
 
-// second-generation warp walker over every ray, chunk by chunk: plan -> walk
+// second-generation warp walker over every ray, chunk by chunk: plan -> walk (ordinary rays) ->
+// walk (all-cones rays).  Counters (unsigned, behind the pass counters): [0] ordinary records
+// [1] all-cones records  [2] / [3] hand-out counters of the two walks  [4] rays left for pass B
+// [5] rays left for the per-thread walker (accumulated over the chunks).
 template <class Op>
 int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsigned long long* stats)
 {
@@ -1292,23 +1314,30 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
     const size_t smem_plan = cx.smem_tables;
     if (smem_plan > 48 * 1024)
         cudaFuncSetAttribute(plan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
-    cudaFuncSetAttribute(walk_warp_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wl.smem);
-    unsigned* wc = reinterpret_cast<unsigned*>(cx.counters + 8);      // [0] records  [1] hand-out counter
+    cudaFuncSetAttribute(walk_warp_kernel<Op, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wl.smem);
+    cudaFuncSetAttribute(walk_warp_kernel<Op, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wl.smem);
+    unsigned* wc = reinterpret_cast<unsigned*>(cx.counters + 8);
     const int64_t chunk = warp_chunk_rays();
     const int sms = num_sms();
+    cudaMemsetAsync(wc, 0, 8 * sizeof(unsigned), cx.st);
     for (int64_t base = 0; base < cx.kr.n; base += chunk) {
         const int64_t n = cx.kr.n - base < chunk ? cx.kr.n - base : chunk;
-        cudaMemsetAsync(wc, 0, 2 * sizeof(unsigned), cx.st);
+        const int64_t cap = (n + 31) / 32 * 32;
+        if (base > 0) cudaMemsetAsync(wc, 0, 4 * sizeof(unsigned), cx.st);
         const int64_t pb = (n + kPlanBlock - 1) / kPlanBlock;
         plan_warp_kernel<<<(unsigned)pb, kPlanBlock, smem_plan, cx.st>>>(
-            *cx.grid, cx.kr, base, n, wl.caps, cx.recs, wc, cx.mask_listed, cx.mask_tracked,
+            *cx.grid, cx.kr, base, n, wl.caps, cx.recs, wc, cap, cx.mask_listed, cx.mask_tracked,
             op.miss_count(), stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
         int64_t blocks = (n + (int64_t)wl.P.warps * kWarpBatch - 1) / ((int64_t)wl.P.warps * kWarpBatch);
         if (blocks > sms) blocks = sms;
-        walk_warp_kernel<Op><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
-            *cx.grid, cx.kr.starts, op, wl.P, cx.recs, wc, base, cx.mask_tracked, wc + 1, stats);
+        walk_warp_kernel<Op, false><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
+            *cx.grid, cx.kr.starts, op, wl.P, cx.recs, wc, base, cx.mask_tracked, wc + 2, wc + 5, stats);
+        rc = cuda_status();
+        if (rc != SPHRT_OK) return rc;
+        walk_warp_kernel<Op, true><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
+            *cx.grid, cx.kr.starts, op, wl.P, cx.recs + (cap - 1), wc + 1, base, cx.mask_listed, wc + 3, wc + 4, stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
     }
@@ -1316,7 +1345,7 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
 }
 
 template <class Op>
-int launch_tracked_masked(const PassContext& cx, const Op& op)
+int launch_tracked_masked(const PassContext& cx, const Op& op, const unsigned* n_work = nullptr)
 {
     const size_t smem = cx.smem_tables + kQueueBytes;
     if (smem > 40 * 1024)   // (+ the static flag queue)
@@ -1327,7 +1356,7 @@ int launch_tracked_masked(const PassContext& cx, const Op& op)
     if (blocks < 1) blocks = 1;
     walk_tracked_masked_kernel<Op><<<(unsigned)blocks, kBlock, smem, cx.st>>>(
         *cx.grid, cx.kr, op, (int)(cx.smem_tables / sizeof(double)), cx.mask_tracked, cx.n_words,
-        cx.counters + 1);
+        cx.counters + 1, n_work);
     return cuda_status();
 }
 
@@ -1378,12 +1407,12 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
         const CoopLaunch cl = plan_coop(*grid, rays->n_rays);
         if (cl.ok && (force_coop || want_coop(*grid, rays->walker))) {
             const WarpLaunch wl = plan_warp(*grid);
+            const unsigned* wc = nullptr;          // gen 2 counts the rays it leaves for the fallback passes
             if (wl.ok && want_warp_gen2()) {
+                wc = reinterpret_cast<unsigned*>(cx.counters + 8);
                 // ordinary rays: plan + walk kernels of sphrt_warp.cuh; then the all-cones rays,
                 // in place on their mask
                 rc = launch_warp(cx, wl, op, stats);
-                if (rc == SPHRT_OK)
-                    rc = launch_coop<Op, COOP_ALLCONES>(cx, cl, op, cx.mask_listed, cx.counters + 3, stats);
             } else if (rays->n_rays < coop_split_rays()) {
                 rc = launch_coop<Op, COOP_BOTH>(cx, cl, op, nullptr, cx.counters, stats);
             } else {
@@ -1396,10 +1425,10 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
             if constexpr (Op::kEvents) {
                 return SPHRT_OK;               // raw event export: cooperative walker only
             } else {
-                rc = launch_tracked_masked(cx, op);
+                rc = launch_tracked_masked(cx, op, wc ? wc + 5 : nullptr);
                 if (rc != SPHRT_OK) return rc;
                 return launch_listed(grid, cx.kr, op, cx.mask_listed, cx.lists, cx.smem_tables, lp,
-                                     cx.counters + 2, cx.st);
+                                     cx.counters + 2, cx.st, wc ? wc + 4 : nullptr);
             }
         }
     }

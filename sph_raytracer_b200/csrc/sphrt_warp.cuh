@@ -171,7 +171,12 @@ __device__ __forceinline__ void warp_seam_plane(const Tab32& T, const RayConsts&
     geo = ev.geo;
 }
 
-template <bool kEvents, class Sink>
+// kAllCones: the rays whose cone roots lose adjacency (snapped discriminant or leading coefficient,
+// ray_needs_cone_list) or that start ON a cone / half-plane: walked from the START point (t = 0)
+// with EVERY cone evaluated and the valid roots put in order by an explicit rank sort -- the
+// reference's algorithm (:131) restricted to the elevation family -- instead of the candidate range
+// around the turning point.  Everything after the elevation list is the same code.
+template <bool kEvents, bool kAllCones, class Sink>
 __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, uint32_t wbase,
                                              const PlanRec& R, const double* xs, int lane, uint32_t lt_mask,
                                              Sink& sink)
@@ -192,7 +197,7 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     double t_in, t_out;
     {
         const double sN = sqrt(lds_f64(T.r2 + 8u * T.nr) - c.dperp2);
-        t_in = c.tc - sN; t_out = c.tc + sN;
+        t_in = kAllCones ? 0.0 : c.tc - sN; t_out = c.tc + sN;
     }
 
     // ---- elevation: candidates from the turning point outwards (as coop_build)
@@ -201,7 +206,55 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     const int e_mid = R.e_mid;
     int nDown = 0, nUp = 0;
     bool unchanged = false;
-    {
+    if constexpr (kAllCones) {
+        // every cone, both roots, unsorted into the (still unused) merge buffers ...
+        const uint32_t tmpT = wbase + P.off_tEA, tmpR = wbase + P.off_sEA + 4u;
+        int n = 0;
+#pragma unroll 1
+        for (int i = lane; __any_sync(SPHRT_FULL, i <= T.ne); i += 32) {
+            double t1 = SPHRT_INF, t2 = SPHRT_INF;
+            bool v1 = false, v2 = false;
+            if (i <= T.ne) {
+                double c2, sgn;
+                lds_f64x2(T.cone + 16u * i, c2, sgn);
+                const ConeQuad q = cone_quadratic_c2(c, c2);
+                cone_roots_guarded(q, fabs(q.delta) < SPHRT_TAU ? 0.0 : q.delta, t1, t2);
+                v1 = t1 >= t_in && t1 <= t_out && !cone_shadow_sgn(c, sgn, t1);
+                v2 = t2 >= t_in && t2 <= t_out && !cone_shadow_sgn(c, sgn, t2);
+            }
+            const uint32_t m1 = __ballot_sync(SPHRT_FULL, v1), m2 = __ballot_sync(SPHRT_FULL, v2);
+            const int s1 = n + __popc(m1 & lt_mask), s2 = n + __popc(m1) + __popc(m2 & lt_mask);
+            int geo;
+            if (v1) {
+                if (s1 < P.capE) { sts_f64(tmpT + 8u * s1, t1); sts_s32(tmpR + 4u * s1, cone_region_ne(T.ne, c, i, t1, &geo)); }
+                else bad = true;
+            }
+            if (v2) {
+                if (s2 < P.capE) { sts_f64(tmpT + 8u * s2, t2); sts_s32(tmpR + 4u * s2, cone_region_ne(T.ne, c, i, t2, &geo)); }
+                else bad = true;
+            }
+            n += __popc(m1) + __popc(m2);
+        }
+        __syncwarp();
+        // ... then to their rank (the reference's sort, :131; ties in evaluation order)
+        if (n <= P.capE) {
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) {
+                const double te = lds_f64(tmpT + 8u * e);
+                int rank = 0;
+#pragma unroll 1
+                for (int j = 0; j < n; j++) {
+                    const double tj = lds_f64(tmpT + 8u * j);
+                    rank += (tj < te || (tj == te && j < e)) ? 1 : 0;
+                }
+                const int reg = lds_s32(tmpR + 4u * e);
+                sts_f64(tEbuf + 8u * rank, te);
+                sts_s32(rEbuf + 4u * rank, reg >= 0 ? reg * na : (reg == -2 ? kUnchangedState : kInvalidState));
+                unchanged |= reg == -2;
+            }
+        } else bad = true;
+        nUp = n;
+    } else {
         int k = lane, i = R.e_first + lane * e_step;
         const int i_step = 32 * e_step;
 #pragma unroll 1
