@@ -82,6 +82,22 @@ typedef struct sphrt_rays {
                                 * 1 = warp-cooperative, 2 = per-thread.  Same results either way;
                                 * the caller may time both once and keep the faster one (the Python
                                 * Operator does).  SPHRT_WALKER in the environment overrides. */
+    /* Optional analytic ray generation for pinhole detectors: instead of
+     * `dirs` (24 bytes per ray, 6.3 GB at config 5) the directions are formed inside the kernels
+     * from a 96-byte frame per observation and float32 pixel-coordinate tables, with exactly the
+     * arithmetic of the reference's detector classes (geometry.py:494-508 rectangular,
+     * :573-582 polar), so that they are bit-identical to geom.rays:
+     *     d = (lookdir + A * u) + B * v ;  d /= sqrt(fma(d2, d2, fma(d1, d1, d0 * d0)))
+     *     gen_kind 1 (ConeRectGeom): A = ta[row], B = tb[col]
+     *     gen_kind 2 (ConeCircGeom): A = ta[row] * tb[col], B = ta[row] * tc[col]  (float32 products)
+     * Ray i belongs to observation i / (gen_h * gen_w), row (i / gen_w) % gen_h, column i % gen_w;
+     * `starts` holds the pinhole of every observation (rays_per_start == gen_h * gen_w).
+     * gen_kind 0: `dirs` is used. */
+    int32_t gen_kind, gen_h, gen_w, gen_per_obs_tables;
+    const double *gen_frames;  /* (n_obs, 12): pos, lookdir, u = lookdir x updir, v = updir      */
+    const float *gen_ta;       /* (gen_h) rows, or (n_obs, gen_h) if gen_per_obs_tables          */
+    const float *gen_tb;       /* (gen_w) columns, or (n_obs, gen_w)                             */
+    const float *gen_tc;       /* polar detectors only                                           */
 } sphrt_rays;
 
 /* Bytes of caller-owned scratch the tracing entry points need for this grid and ray count:
@@ -174,6 +190,10 @@ int sphrt_walker_kind(const sphrt_grid *grid, int64_t n_rays);
  * for "outside" exactly like the reference. */
 int sphrt_find_starts(const sphrt_grid *grid, int64_t n, const double *xs, int32_t *out,
                       void *stream);
+
+/* The direction of every ray as the kernels see it, (n_rays, 3) float64: `dirs` broadcast, or the
+ * analytically generated directions (parity export: they must equal geom.rays bit for bit). */
+int sphrt_export_rays(const sphrt_rays *rays, double *dirs_out, void *stream);
 
 int sphrt_version(void);
 const char *sphrt_error_string(int code);

@@ -16,7 +16,7 @@ EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphr
            "sphrt_forward", "sphrt_adjoint", "sphrt_count_segments", "sphrt_trace_segments",
            "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind",
            "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates",
-           "sphrt_launch_count")
+           "sphrt_launch_count", "sphrt_export_rays")
 
 
 class Grid(ctypes.Structure):
@@ -30,7 +30,9 @@ class Rays(ctypes.Structure):
     """struct sphrt_rays"""
     _fields_ = [("n_rays", c_int64), ("starts", c_void_p), ("rays_per_start", c_int64),
                 ("dirs", c_void_p), ("rays_per_dir", c_int64), ("start_cells", c_void_p),
-                ("walker", c_int64)]
+                ("walker", c_int64),
+                ("gen_kind", c_int32), ("gen_h", c_int32), ("gen_w", c_int32), ("gen_per_obs_tables", c_int32),
+                ("gen_frames", c_void_p), ("gen_ta", c_void_p), ("gen_tb", c_void_p), ("gen_tc", c_void_p)]
 
 
 class SphrtError(RuntimeError):
@@ -89,6 +91,8 @@ def load(path=None):
     lib.sphrt_walker_kind.argtypes = [P(Grid), c_int64]
     lib.sphrt_find_starts.restype = c_int
     lib.sphrt_find_starts.argtypes = [P(Grid), c_int64, c_void_p, c_void_p, c_void_p]
+    lib.sphrt_export_rays.restype = c_int
+    lib.sphrt_export_rays.argtypes = [P(Rays), c_void_p, c_void_p]
     _lib = lib
     return lib
 

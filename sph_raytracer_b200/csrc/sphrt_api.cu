@@ -117,8 +117,7 @@ int sphrt_candidates(const sphrt_grid* grid, const sphrt_rays* rays, double* t, 
     rc = check_rays(rays); if (rc) return rc;
     if (rays->n_rays == 0) return SPHRT_OK;
     if (!t || !region || !geo) return SPHRT_EINVAL;
-    const KRays kr{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
-                   rays->start_cells};
+    const KRays kr = make_krays(rays);
     const size_t smem = (size_t)table_doubles(*grid) * sizeof(double);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -137,6 +136,17 @@ int sphrt_find_starts(const sphrt_grid* grid, int64_t n, const double* xs, int32
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(find_starts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     find_starts_kernel<<<(unsigned)blocks, kBlock, smem, (cudaStream_t)stream>>>(*grid, n, xs, out);
+    return cuda_status();
+}
+
+int sphrt_export_rays(const sphrt_rays* rays, double* dirs_out, void* stream)
+{
+    int rc = check_rays(rays); if (rc) return rc;
+    if (rays->n_rays == 0) return SPHRT_OK;
+    if (!dirs_out) return SPHRT_EINVAL;
+    const KRays kr = make_krays(rays);
+    const int64_t blocks = (rays->n_rays + 255) / 256;
+    export_rays_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(kr, dirs_out);
     return cuda_status();
 }
 

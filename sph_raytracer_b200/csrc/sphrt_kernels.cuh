@@ -58,7 +58,17 @@ struct KRays {
     const double* starts; int64_t rps;
     const double* dirs; int64_t rpd;
     const int32_t* cells;          // host-evaluated find_starts of every start row (may be null)
+    // analytic ray generation (sphrt_rays::gen_*): 0 = directions come from `dirs`
+    int gen_kind, gen_h, gen_w, gen_per_obs;
+    const double* frames; const float* ta; const float* tb; const float* tc;
 };
+
+inline KRays make_krays(const sphrt_rays* r)
+{
+    return KRays{r->n_rays, r->starts, r->rays_per_start, r->dirs, r->rays_per_dir, r->start_cells,
+                 r->gen_kind, r->gen_h, r->gen_w, r->gen_per_obs_tables,
+                 r->gen_frames, r->gen_ta, r->gen_tb, r->gen_tc};
+}
 
 // Start voxel of ray i: from the caller's table (the reference's own binning) or, without one,
 // evaluated here.
@@ -101,12 +111,50 @@ __device__ __forceinline__ GridView stage_tables(const sphrt_grid& kg, double* s
     return g;
 }
 
+// Direction of pixel (row, col) of a pinhole detector exactly as the reference's detector classes
+// form it (geometry.py:494-508, 573-582): float32 pixel coordinates promoted on multiply, two
+// products and two sums in float64 left to right, then the 3-vector normalisation of
+// torch.linalg.norm (fused sum of squares).
+__device__ __forceinline__ void generate_ray(const KRays& kr, int64_t i, double d[3])
+{
+    const int64_t hw = (int64_t)kr.gen_h * kr.gen_w;
+    const int64_t obs = i / hw;
+    const int rem = (int)(i - obs * hw);
+    const int row = rem / kr.gen_w, col = rem - row * kr.gen_w;
+    const double* f = kr.frames + 12 * obs;
+    const int64_t ot = kr.gen_per_obs ? obs : 0;
+    const float a_row = __ldg(kr.ta + ot * kr.gen_h + row);
+    float A, B;
+    if (kr.gen_kind == 2) {
+        A = __fmul_rn(a_row, __ldg(kr.tb + ot * kr.gen_w + col));
+        B = __fmul_rn(a_row, __ldg(kr.tc + ot * kr.gen_w + col));
+    } else {
+        A = a_row;
+        B = __ldg(kr.tb + ot * kr.gen_w + col);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        d[k] = (__ldg(f + 3 + k) + __ldg(f + 6 + k) * (double)A) + __ldg(f + 9 + k) * (double)B;
+    const double n = norm3(d[0], d[1], d[2]);
+    d[0] /= n; d[1] /= n; d[2] /= n;
+}
+
 __device__ __forceinline__ void load_ray(const KRays& kr, int64_t i, double x[3], double d[3])
 {
     const double* xs = kr.starts + 3 * (i / kr.rps);
-    const double* ds = kr.dirs + 3 * (i / kr.rpd);
     x[0] = __ldg(xs); x[1] = __ldg(xs + 1); x[2] = __ldg(xs + 2);
+    if (kr.gen_kind != 0) { generate_ray(kr, i, d); return; }
+    const double* ds = kr.dirs + 3 * (i / kr.rpd);
     d[0] = __ldg(ds); d[1] = __ldg(ds + 1); d[2] = __ldg(ds + 2);
+}
+
+__global__ void export_rays_kernel(KRays kr, double* out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kr.n) return;
+    double x[3], d[3];
+    load_ray(kr, i, x, d);
+    out[3 * i] = d[0]; out[3 * i + 1] = d[1]; out[3 * i + 2] = d[2];
 }
 
 // ---- per-ray operations ------------------------------------------------------------------
@@ -1232,8 +1280,14 @@ int check_grid(const sphrt_grid* g)
 int check_rays(const sphrt_rays* r)
 {
     if (r == nullptr || r->n_rays < 0) return SPHRT_EINVAL;
-    if (r->n_rays > 0 && (!r->starts || !r->dirs || r->rays_per_start < 1 || r->rays_per_dir < 1))
-        return SPHRT_EINVAL;
+    if (r->n_rays > 0 && (!r->starts || r->rays_per_start < 1)) return SPHRT_EINVAL;
+    if (r->gen_kind == 0) {
+        if (r->n_rays > 0 && (!r->dirs || r->rays_per_dir < 1)) return SPHRT_EINVAL;
+    } else {
+        if (r->gen_kind < 0 || r->gen_kind > 2 || r->gen_h < 1 || r->gen_w < 1) return SPHRT_EINVAL;
+        if (!r->gen_frames || !r->gen_ta || !r->gen_tb || (r->gen_kind == 2 && !r->gen_tc)) return SPHRT_EINVAL;
+        if (r->n_rays % ((int64_t)r->gen_h * r->gen_w) != 0) return SPHRT_EINVAL;
+    }
     if (r->walker < 0 || r->walker > 2) return SPHRT_EINVAL;
     return SPHRT_OK;
 }
@@ -1389,8 +1443,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
     if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
     PassContext cx;
     cx.grid = grid;
-    cx.kr = KRays{rays->n_rays, rays->starts, rays->rays_per_start, rays->dirs, rays->rays_per_dir,
-                  rays->start_cells};
+    cx.kr = make_krays(rays);
     cx.st = (cudaStream_t)stream;
     cx.smem_tables = (size_t)table_doubles(*grid) * sizeof(double);
     cx.mask_listed = (uint32_t*)scratch;

@@ -18,7 +18,7 @@ import math
 import torch
 
 from . import _cabi
-from .geometry import ViewGeomCollection
+from .geometry import ViewGeomCollection, ConeRectGeom, ConeCircGeom
 
 __all__ = ["Operator", "find_starts", "find_starts_cuda", "r_torch", "e_torch", "a_torch", "DEVICE", "FTYPE", "ITYPE"]
 
@@ -111,28 +111,94 @@ def _start_cells(r_b, e_b, a_b, starts):
     return cells
 
 
+def _pinhole_generator(geom):
+    """Analytic description of a pinhole detector or a collection of them: per
+    observation the frame (pos, lookdir, u, v) the reference's ``rays`` property starts from, and
+    the float32 pixel-coordinate tables it multiplies them with (reference geometry.py:494-508
+    rectangular, :557-568, 573-582 polar).  The kernels then form every direction themselves,
+    bit-identical to ``geom.rays``, and ``geom.rays`` is never materialised.  None if ``geom`` is
+    not made of such detectors (or they differ in shape)."""
+    obs = list(geom.geoms) if isinstance(geom, ViewGeomCollection) else [geom]
+    if not obs or not all(type(g) in (ConeRectGeom, ConeCircGeom) for g in obs):
+        return None
+    if len({(type(g), tuple(g.shape)) for g in obs}) != 1 or len(obs[0].shape) != 2:
+        return None
+    polar = type(obs[0]) is ConeCircGeom
+    H, W = (int(v) for v in obs[0].shape)
+    frames, ta, tb, tc = [], [], [], []
+    for g in obs:
+        u = torch.cross(g.lookdir, g.updir, dim=-1)
+        frames.append(torch.cat([g.pos.reshape(3), g.lookdir.reshape(3), u.reshape(3), g.updir.reshape(3)]))
+        if polar:
+            ta.append(g.r.to(torch.float32)); tb.append(torch.cos(g.theta)); tc.append(torch.sin(g.theta))
+        else:
+            ta.append(torch.linspace(-g._half_extent(0), g._half_extent(0), H))
+            tb.append(torch.linspace(-g._half_extent(1), g._half_extent(1), W))
+    if any(t.dtype != torch.float32 for t in ta + tb + tc):
+        return None
+    same = all(torch.equal(t, ta[0]) for t in ta) and all(torch.equal(t, tb[0]) for t in tb) and \
+        all(torch.equal(t, tc[0]) for t in tc)
+    keep = (lambda ts: ts[0][None]) if same else torch.stack
+    lead = (len(obs),) if isinstance(geom, ViewGeomCollection) else ()
+    return {"kind": 2 if polar else 1, "H": H, "W": W, "per_obs": 0 if same else 1,
+            "frames": torch.stack(frames).to(torch.float64).contiguous(),
+            "ta": keep(ta).contiguous(), "tb": keep(tb).contiguous(),
+            "tc": keep(tc).contiguous() if polar else None,
+            "shape": lead + (H, W)}
+
+
 class _Rays:
-    """Ray origins and directions of a view geometry on the GPU (float64)."""
+    """Ray origins and directions of a view geometry on the GPU (float64).
+
+    Pinhole detectors (ConeRectGeom / ConeCircGeom and collections of them) are described
+    analytically: 96 bytes per observation plus the pixel-coordinate tables instead of 24 bytes per
+    ray; SPHRT_RAYGEN=0 uploads explicit directions as for any other geometry."""
 
     def __init__(self, geom, device, tables=None):
-        starts = torch.asarray(geom.ray_starts, dtype=torch.float64)
-        dirs = torch.asarray(geom.rays, dtype=torch.float64)
-        # the reference broadcasts the smaller of the two to the larger (raytracer.py:77-80)
-        full = tuple(starts.shape if starts.numel() > dirs.numel() else dirs.shape)[:-1]
-        if max(starts.dim(), dirs.dim()) - 1 > len(full):
-            raise ValueError(f"ray_starts {tuple(starts.shape)} and rays {tuple(dirs.shape)} "
-                             "cannot be broadcast to a common detector shape")
-        self.shape = tuple(full)
-        self.n = math.prod(self.shape)
-        s, self.rays_per_start = _compact(starts, self.shape)
-        d, self.rays_per_dir = _compact(dirs, self.shape)
-        self.starts, self.dirs = s.to(device), d.to(device)
+        import os
+        gen = _pinhole_generator(geom) if os.environ.get("SPHRT_RAYGEN", "1") != "0" else None
         self.cells = None
+        if gen is not None:
+            self.shape = tuple(gen["shape"])
+            self.n = math.prod(self.shape)
+            s = gen["frames"][:, :3].contiguous()
+            self.rays_per_start, self.rays_per_dir = gen["H"] * gen["W"], 1
+            self.starts, self.dirs = s.to(device), None
+            self._gen = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in gen.items()}
+        else:
+            starts = torch.asarray(geom.ray_starts, dtype=torch.float64)
+            dirs = torch.asarray(geom.rays, dtype=torch.float64)
+            # the reference broadcasts the smaller of the two to the larger (raytracer.py:77-80)
+            full = tuple(starts.shape if starts.numel() > dirs.numel() else dirs.shape)[:-1]
+            if max(starts.dim(), dirs.dim()) - 1 > len(full):
+                raise ValueError(f"ray_starts {tuple(starts.shape)} and rays {tuple(dirs.shape)} "
+                                 "cannot be broadcast to a common detector shape")
+            self.shape = tuple(full)
+            self.n = math.prod(self.shape)
+            s, self.rays_per_start = _compact(starts, self.shape)
+            d, self.rays_per_dir = _compact(dirs, self.shape)
+            self.starts, self.dirs = s.to(device), d.to(device)
+            self._gen = None
         if tables is not None:
             self.cells = _start_cells(tables.r_b, tables.e_b, tables.a_b, s.cpu()).to(device)
-        self.c = _cabi.Rays(self.n, self.starts.data_ptr(), self.rays_per_start,
-                            self.dirs.data_ptr(), self.rays_per_dir,
-                            self.cells.data_ptr() if self.cells is not None else None, 0)
+        self.c = self.struct(self.n)
+
+    def struct(self, n_rays, walker=0):
+        """``struct sphrt_rays`` of the first ``n_rays`` rays."""
+        g = self._gen
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        return _cabi.Rays(n_rays, self.starts.data_ptr(), self.rays_per_start,
+                          ptr(self.dirs), self.rays_per_dir, ptr(self.cells), walker,
+                          g["kind"] if g else 0, g["H"] if g else 0, g["W"] if g else 0, g["per_obs"] if g else 0,
+                          ptr(g["frames"]) if g else None, ptr(g["ta"]) if g else None,
+                          ptr(g["tb"]) if g else None, ptr(g["tc"]) if g else None)
+
+    def directions(self, lib, stream):
+        """Every ray's direction as the kernels see it, ``(*shape, 3)`` float64 (parity export)."""
+        out = torch.empty((self.n, 3), dtype=torch.float64, device=self.starts.device)
+        with torch.cuda.device(out.device):
+            _cabi.check(lib.sphrt_export_rays(self.c, out.data_ptr(), stream))
+        return out.reshape(self.shape + (3,))
 
 
 class _LineIntegral(torch.autograd.Function):
@@ -221,8 +287,11 @@ class Operator:
         if os.environ.get("SPHRT_AUTOTUNE", "1") == "0" or os.environ.get("SPHRT_WALKER") or self._rays.n < 4096:
             return
         r, t = self._rays, self._tables
-        probe = _cabi.Rays(min(r.n, max_rays), r.starts.data_ptr(), r.rays_per_start,
-                           r.dirs.data_ptr(), r.rays_per_dir, r.c.start_cells, 0)
+        n_probe = min(r.n, max_rays)
+        if r._gen is not None:                      # whole observations
+            hw = r._gen["H"] * r._gen["W"]
+            n_probe = max(hw, n_probe // hw * hw)
+        probe = r.struct(n_probe)
         vol = torch.ones(t.nvox, dtype=torch.float32, device=self._cdev)
         out = torch.empty(probe.n_rays, dtype=torch.float32, device=self._cdev)
         scratch = self._scratch()
