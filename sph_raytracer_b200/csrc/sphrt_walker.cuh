@@ -199,7 +199,9 @@ SPHRT_HD void cone_roots(const ConeQuad& q, double delta, double& t1, double& t2
 SPHRT_HD void cone_roots_guarded(const ConeQuad& q, double delta, double& t1, double& t2)
 {
     const bool none = !(delta >= 0);
-    const double sq = sqrt(none ? 0.0 : delta);
+    // (sqrt(0) itself takes the slow path too: 1.0 stands in for both and the zero is put back)
+    double sq = sqrt(none || delta == 0 ? 1.0 : delta);
+    if (delta == 0) sq = 0.0;
     t1 = (-q.bb + sq) / (2 * q.aa);
     t2 = (-q.bb - sq) / (2 * q.aa);
     if (none) { t1 = __builtin_nan(""); t2 = __builtin_nan(""); }
