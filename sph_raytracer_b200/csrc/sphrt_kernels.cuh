@@ -972,12 +972,17 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
     auto rec_at = [&](unsigned k) { return kAllCones ? recs - k : recs + k; };
     // batches are handed out one ahead: the atomic and the record prefetch of the next batch are
     // in flight while the current one is walked
+    // (records per hand-out: kWarpBatch when every warp gets many batches; small launches -- a few
+    // records per warp, like the all-cones rays of a 50^3 problem -- take them one or two at a time,
+    // or most warps would idle while a few walk eight rays in a row)
+    unsigned batch = n_recs / (8u * gridDim.x * (blockDim.x >> 5));
+    batch = batch < 1u ? 1u : (batch > kWarpBatch ? kWarpBatch : batch);
     auto grab = [&]() {
         unsigned v = 0;
-        if (lane == 0) v = atomicAdd(counter, kWarpBatch);
+        if (lane == 0) v = atomicAdd(counter, batch);
         v = __shfl_sync(0xffffffffu, v, 0);
         if (v < n_recs && lane < 6) {
-            const unsigned e = v + kWarpBatch < n_recs ? v + kWarpBatch : n_recs;
+            const unsigned e = v + batch < n_recs ? v + batch : n_recs;
             const PlanRec* first = kAllCones ? rec_at(e - 1) : rec_at(v);       // lowest address of the batch
             const char* p = reinterpret_cast<const char*>(first) + 128 * lane;
             if (p < reinterpret_cast<const char*>(first + (e - v))) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
@@ -986,7 +991,7 @@ walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPl
     };
     unsigned b = grab();
     while (b < n_recs) {
-        const unsigned e = b + kWarpBatch < n_recs ? b + kWarpBatch : n_recs;
+        const unsigned e = b + batch < n_recs ? b + batch : n_recs;
         const unsigned b_next = grab();
         for (unsigned k = b; k < e; k++) {
             const PlanRec R = load_plan_rec(rec_at(k));
