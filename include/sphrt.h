@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 4
+#define SPHRT_VERSION 5
 
 enum {
     SPHRT_OK = 0,
@@ -157,6 +157,32 @@ int sphrt_forward_stored(const int64_t *offsets, const int32_t *vox, const void 
 int sphrt_adjoint_stored(const int64_t *offsets, const int32_t *vox, const void *seg_len, int len_dtype,
                          int64_t n_rays, const void *y, int dtype, int64_t n_vol,
                          int64_t rays_per_vol, int64_t nvox, void *grad, void *stream);
+
+/* Packed stored operator: 4 bytes per segment, for the observations that fit in device memory
+ * when the operator is applied many times (a retrieval loop; the reference stores its operator
+ * at 32 bytes per padded slot, raytracer.py:66-72, 675-679, and applies it with a gather,
+ * :710-713).  One 32-bit word per canonical segment: bits 31..29 a step code relative to the
+ * previous voxel of the ray (0/1 = +-1 azimuth, 2/3 = +-na elevation, 4/5 = +-ne*na radial, in
+ * flat voxel offsets (r*ne + e)*na + a; 6 = same voxel), bits 28..0 the length as a float32
+ * rounded to 29 bits (bits << 2 is the float; relative error 2.4e-7).  Code 7 is an escape: bits
+ * 28..0 are an absolute voxel offset, no length (first voxel of a ray, azimuth seam, holes,
+ * diagonal moves); the next word is a code-6 word with the length.  Needs nr*ne*na < 2^29.
+ * sphrt_pack_count: words per ray (count, n_rays int32) and their sum (total, may be NULL;
+ * caller zero-fills); offsets (n_rays + 1) int64 = exclusive prefix sum of count;
+ * sphrt_pack_segments writes the words; sphrt_forward_packed / sphrt_adjoint_packed apply them
+ * like sphrt_forward / sphrt_adjoint (same n_vol / rays_per_vol rules, float32 or float64
+ * volumes).  A caller may pack a PREFIX of its rays (whole observations) and trace the rest with
+ * sphrt_forward / sphrt_adjoint on a sphrt_rays that starts at the first unpacked observation. */
+int sphrt_pack_count(const sphrt_grid *grid, const sphrt_rays *rays, int32_t *count,
+                     unsigned long long *total, void *scratch, int64_t scratch_bytes, void *stream);
+int sphrt_pack_segments(const sphrt_grid *grid, const sphrt_rays *rays, const int64_t *offsets,
+                        uint32_t *words, void *scratch, int64_t scratch_bytes, void *stream);
+int sphrt_forward_packed(const int64_t *offsets, const uint32_t *words, int64_t n_rays, int ne, int na,
+                         const void *density, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                         int64_t nvox, void *out, void *stream);
+int sphrt_adjoint_packed(const int64_t *offsets, const uint32_t *words, int64_t n_rays, int ne, int na,
+                         const void *y, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                         int64_t nvox, void *grad, void *stream);
 
 /* Parity export of the warp-cooperative walker (the kernel that serves large grids): for
  * every ray it handles itself, ALL its events in merged order -- the reference's sorted

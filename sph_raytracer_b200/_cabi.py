@@ -16,7 +16,8 @@ EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphr
            "sphrt_forward", "sphrt_adjoint", "sphrt_count_segments", "sphrt_trace_segments",
            "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind",
            "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates",
-           "sphrt_launch_count", "sphrt_export_rays")
+           "sphrt_launch_count", "sphrt_export_rays",
+           "sphrt_pack_count", "sphrt_pack_segments", "sphrt_forward_packed", "sphrt_adjoint_packed")
 
 
 class Grid(ctypes.Structure):
@@ -85,6 +86,16 @@ def load(path=None):
     lib.sphrt_forward_stored.argtypes = stored_args
     lib.sphrt_adjoint_stored.restype = c_int
     lib.sphrt_adjoint_stored.argtypes = stored_args
+    lib.sphrt_pack_count.restype = c_int
+    lib.sphrt_pack_count.argtypes = [P(Grid), P(Rays), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.sphrt_pack_segments.restype = c_int
+    lib.sphrt_pack_segments.argtypes = [P(Grid), P(Rays), c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    packed_args = [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64,
+                   c_int64, c_void_p, c_void_p]
+    lib.sphrt_forward_packed.restype = c_int
+    lib.sphrt_forward_packed.argtypes = packed_args
+    lib.sphrt_adjoint_packed.restype = c_int
+    lib.sphrt_adjoint_packed.argtypes = packed_args
     lib.sphrt_candidates.restype = c_int
     lib.sphrt_candidates.argtypes = [P(Grid), P(Rays), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sphrt_walker_kind.restype = c_int

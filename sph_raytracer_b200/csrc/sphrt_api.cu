@@ -92,6 +92,42 @@ int sphrt_adjoint_stored(const int64_t* offsets, const int32_t* vox, const void*
                                  rays_per_vol, nvox, stream);
 }
 
+int sphrt_pack_count(const sphrt_grid* grid, const sphrt_rays* rays, int32_t* count,
+                     unsigned long long* total, void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if ((int64_t)grid->nr * grid->ne * grid->na > (int64_t)kPackLenMask) return SPHRT_ETOOBIG;
+    if (rays->n_rays > 0 && !count) return SPHRT_EINVAL;
+    const PackOp<false> op{nullptr, nullptr, count, total, grid->ne, grid->na};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_pack_segments(const sphrt_grid* grid, const sphrt_rays* rays, const int64_t* offsets,
+                        uint32_t* words, void* scratch, int64_t scratch_bytes, void* stream)
+{
+    int rc = check_grid(grid); if (rc) return rc;
+    rc = check_rays(rays); if (rc) return rc;
+    if ((int64_t)grid->nr * grid->ne * grid->na > (int64_t)kPackLenMask) return SPHRT_ETOOBIG;
+    if (rays->n_rays > 0 && (!offsets || !words)) return SPHRT_EINVAL;
+    const PackOp<true> op{offsets, words, nullptr, nullptr, grid->ne, grid->na};
+    return launch_passes(grid, rays, op, scratch, scratch_bytes, stream);
+}
+
+int sphrt_forward_packed(const int64_t* offsets, const uint32_t* words, int64_t n_rays, int ne, int na,
+                         const void* density, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                         int64_t nvox, void* out, void* stream)
+{
+    return dispatch_packed<false>(offsets, words, n_rays, ne, na, density, dtype, out, n_vol, rays_per_vol, nvox, stream);
+}
+
+int sphrt_adjoint_packed(const int64_t* offsets, const uint32_t* words, int64_t n_rays, int ne, int na,
+                         const void* y, int dtype, int64_t n_vol, int64_t rays_per_vol,
+                         int64_t nvox, void* grad, void* stream)
+{
+    return dispatch_packed<true>(offsets, words, n_rays, ne, na, y, dtype, grad, n_vol, rays_per_vol, nvox, stream);
+}
+
 int sphrt_trace_events(const sphrt_grid* grid, const sphrt_rays* rays, int64_t max_ev,
                        int32_t* vox, double* ev_len, int32_t* count, unsigned long long* stats,
                        void* scratch, int64_t scratch_bytes, void* stream)

@@ -1556,6 +1556,82 @@ int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in
 // ---- stored operator: apply passes ---------------------------------------------------------------
 // One warp per ray streams the ray's (voxel, length) pairs with coalesced loads; the volume is
 // gathered from L2.  Bound by HBM: 8 B (12 B for float64 lengths) per segment.
+// Packed stored operator: 4 bytes per segment.  Along a ray the canonical segments visit voxels
+// that almost always differ from their predecessor by one step along one axis, so a segment is ONE
+// 32-bit word: a 3-bit step code (+-1 azimuth, +-na elevation, +-ne*na radial, flat voxel offsets)
+// and its length as a float32 rounded to 29 bits (sign bit and two mantissa bits dropped: relative
+// 2.4e-7).  Anything else -- the first voxel of a ray, the azimuth seam, a hole between two valid
+// voxels (inner shell, gap sector), a diagonal move after an exact tie -- is an escape word that
+// carries the absolute voxel offset, followed by a "stay" word with the length.  The reference
+// stores 32 bytes for each of its K padded slots per ray (raytracer.py:66-72, 675-679).
+constexpr uint32_t kPackLenMask = 0x1fffffffu;
+enum { PACK_STAY = 6, PACK_ESC = 7 };
+
+__host__ __device__ __forceinline__ int pack_code(int d, int na, int nena)
+{
+    if (d == 1) return 0;
+    if (d == -1) return 1;
+    if (d == na) return 2;
+    if (d == -na) return 3;
+    if (d == nena) return 4;
+    if (d == -nena) return 5;
+    return PACK_ESC;
+}
+__device__ __forceinline__ int pack_delta(uint32_t code, int na, int nena)
+{
+    const int mag = code < 2u ? 1 : (code < 4u ? na : (code < 6u ? nena : 0));
+    return (code & 1u) ? -mag : mag;
+}
+__device__ __forceinline__ uint32_t pack_len(double l)
+{
+    return (__float_as_uint((float)l) + 2u) >> 2;
+}
+
+// kStore == false: count the words of every ray; true: write them at offsets[ray]
+template <bool kStore>
+struct PackOp {
+    const int64_t* offsets; uint32_t* words; int32_t* count; unsigned long long* total; int ne, na;
+    struct Sink {
+        static constexpr int kDepth = 1;
+        uint32_t* out; int ne, na;
+        int cur, prev; double acc; int n;        // pending segment (consecutive identical voxels merge)
+        __device__ __forceinline__ void put(uint32_t w) { if constexpr (kStore) out[n] = w; n++; }
+        __device__ __forceinline__ void flush()
+        {
+            if (cur < 0) return;
+            const int code = prev < 0 ? (int)PACK_ESC : pack_code(cur - prev, na, ne * na);
+            if (code == PACK_ESC) {
+                put(((uint32_t)PACK_ESC << 29) | (uint32_t)cur);
+                put(((uint32_t)PACK_STAY << 29) | pack_len(acc));
+            } else {
+                put(((uint32_t)code << 29) | pack_len(acc));
+            }
+            prev = cur;
+        }
+        __device__ __forceinline__ void segment(int r, int e, int a, double l)
+        {
+            const int idx = (r * ne + e) * na + a;
+            if (idx == cur) { acc += l; return; }
+            flush();
+            cur = idx; acc = l;
+        }
+    };
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        return Sink{kStore ? words + __ldg(offsets + ray) : nullptr, ne, na, -1, -1, 0.0, 0};
+    }
+    __device__ __forceinline__ void end(int64_t ray, Sink& s) const
+    {
+        s.flush();
+        if constexpr (!kStore) {
+            count[ray] = s.n;
+            if (total != nullptr && s.n > 0) atomicAdd(total, (unsigned long long)s.n);
+        }
+    }
+    static constexpr bool kCoop = false, kEvents = false;
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
+};
+
 constexpr int kStoredBlock = 256;
 
 template <typename T, typename L, bool kAdjoint>
@@ -1604,6 +1680,91 @@ int launch_stored(const int64_t* offsets, const int32_t* vox, const void* seg_le
     stored_apply_kernel<T, L, kAdjoint><<<(unsigned)blocks, kStoredBlock, 0, (cudaStream_t)stream>>>(
         offsets, vox, (const L*)seg_len, n_rays, (const T*)in, (T*)out, n_vol, rays_per_vol, nvox);
     return cuda_status();
+}
+
+// One warp per ray streams its words (coalesced, read once: ld.global.cs), 32 at a time: the voxel
+// offsets are a segmented prefix sum of the step codes (an escape restarts the sum), carried from
+// one group of 32 words to the next; gathers / reductions as in stored_apply_kernel.
+template <typename T, bool kAdjoint>
+__global__ void __launch_bounds__(kStoredBlock)
+packed_apply_kernel(const int64_t* __restrict__ offsets, const uint32_t* __restrict__ words,
+                    int64_t n_rays, int na, int nena, const T* __restrict__ in, T* __restrict__ out,
+                    int64_t n_vol, int64_t rays_per_vol, int64_t nvox)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < n_rays; ray += warps) {
+        const int64_t b = __ldg(offsets + ray), e = __ldg(offsets + ray + 1);
+        if (b == e && kAdjoint) continue;
+        const int64_t v0 = rays_per_vol > 0 ? (ray / rays_per_vol) % n_vol : 0;
+        const int64_t nv = rays_per_vol > 0 ? 1 : n_vol;          // channels share the list
+        for (int64_t v = 0; v < nv; v++) {
+            double w = 0.0, acc = 0.0;
+            const T* vin = nullptr; T* vout = nullptr;
+            if constexpr (kAdjoint) {
+                w = (double)__ldg(in + (rays_per_vol > 0 ? ray : v * n_rays + ray));
+                if (w == 0.0) continue;
+                vout = out + (v0 + v) * nvox;
+            } else {
+                vin = in + (v0 + v) * nvox;
+            }
+            int carry = 0;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                const uint32_t word = k < e ? __ldcs(words + k) : ((uint32_t)PACK_STAY << 29);
+                const uint32_t code = word >> 29, payload = word & kPackLenMask;
+                const bool esc = code == (uint32_t)PACK_ESC;
+                int val = esc ? (int)payload : pack_delta(code, na, nena);
+                int flag = esc ? 1 : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int pv = __shfl_up_sync(0xffffffffu, val, o);
+                    const int pf = __shfl_up_sync(0xffffffffu, flag, o);
+                    if (lane >= o && !flag) { val += pv; flag = pf; }
+                }
+                const int idx = flag ? val : carry + val;
+                carry = __shfl_sync(0xffffffffu, idx, 31);
+                const float len = esc ? 0.0f : __uint_as_float(payload << 2);
+                if (len != 0.0f) {
+                    if constexpr (kAdjoint) atomicAdd(vout + idx, (T)(w * (double)len));
+                    else acc = fma_rn((double)__ldg(vin + idx), (double)len, acc);
+                }
+            }
+            if constexpr (!kAdjoint) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) out[rays_per_vol > 0 ? ray : v * n_rays + ray] = (T)acc;
+            }
+        }
+    }
+}
+
+template <typename T, bool kAdjoint>
+int launch_packed(const int64_t* offsets, const uint32_t* words, int64_t n_rays, int ne, int na,
+                  const void* in, void* out, int64_t n_vol, int64_t rays_per_vol, int64_t nvox, void* stream)
+{
+    if (n_rays == 0) return SPHRT_OK;
+    int64_t blocks = (int64_t)num_sms() * (2048 / kStoredBlock);
+    const int64_t want = (n_rays * 32 + kStoredBlock - 1) / kStoredBlock;
+    if (blocks > want) blocks = want;
+    packed_apply_kernel<T, kAdjoint><<<(unsigned)blocks, kStoredBlock, 0, (cudaStream_t)stream>>>(
+        offsets, words, n_rays, na, ne * na, (const T*)in, (T*)out, n_vol, rays_per_vol, nvox);
+    return cuda_status();
+}
+
+template <bool kAdjoint>
+int dispatch_packed(const int64_t* offsets, const uint32_t* words, int64_t n_rays, int ne, int na,
+                    const void* in, int dtype, void* out, int64_t n_vol, int64_t rays_per_vol,
+                    int64_t nvox, void* stream)
+{
+    if (n_rays < 0 || n_vol < 1 || rays_per_vol < 0 || nvox < 1 || ne < 1 || na < 1) return SPHRT_EINVAL;
+    if (nvox > (int64_t)kPackLenMask) return SPHRT_ETOOBIG;              // 29-bit voxel offsets
+    if (n_rays > 0 && (!offsets || !words || !in || !out)) return SPHRT_EINVAL;
+    if (dtype == SPHRT_F32)
+        return launch_packed<float, kAdjoint>(offsets, words, n_rays, ne, na, in, out, n_vol, rays_per_vol, nvox, stream);
+    if (dtype == SPHRT_F64)
+        return launch_packed<double, kAdjoint>(offsets, words, n_rays, ne, na, in, out, n_vol, rays_per_vol, nvox, stream);
+    return SPHRT_EINVAL;
 }
 
 template <bool kAdjoint>

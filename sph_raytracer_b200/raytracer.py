@@ -193,6 +193,33 @@ class _Rays:
                           ptr(g["frames"]) if g else None, ptr(g["ta"]) if g else None,
                           ptr(g["tb"]) if g else None, ptr(g["tc"]) if g else None)
 
+    @property
+    def unit(self):
+        """Rays per observation: the granularity at which the ray list can be split (a prefix /
+        suffix of whole observations is again a valid ``struct sphrt_rays``)."""
+        if self._gen is not None:
+            return self._gen["H"] * self._gen["W"]
+        u = max(self.rays_per_start, self.rays_per_dir)
+        return u if u % self.rays_per_start == 0 and u % self.rays_per_dir == 0 and self.n % u == 0 else self.n
+
+    def struct_from(self, lo, walker=0):
+        """``struct sphrt_rays`` of the rays ``lo ..`` (``lo`` a multiple of ``unit``)."""
+        if lo % self.unit or not 0 <= lo <= self.n:
+            raise ValueError(f"ray {lo} is not the first ray of an observation ({self.unit} rays each)")
+        g = self._gen
+        at = lambda t, k: (t.data_ptr() + k * t.element_size()) if t is not None else None
+        s0 = lo // self.rays_per_start
+        if g:
+            o = lo // self.unit
+            per = g["per_obs"]
+            return _cabi.Rays(self.n - lo, at(self.starts, 3 * s0), self.rays_per_start, None, self.rays_per_dir,
+                              at(self.cells, 8 * s0), walker, g["kind"], g["H"], g["W"], per,
+                              at(g["frames"], 12 * o), at(g["ta"], per * o * g["H"]),
+                              at(g["tb"], per * o * g["W"]), at(g["tc"], per * o * g["W"]))
+        return _cabi.Rays(self.n - lo, at(self.starts, 3 * s0), self.rays_per_start,
+                          at(self.dirs, 3 * (lo // self.rays_per_dir)), self.rays_per_dir,
+                          at(self.cells, 8 * s0), walker, 0, 0, 0, 0, None, None, None, None)
+
     def directions(self, lib, stream):
         """Every ray's direction as the kernels see it, ``(*shape, 3)`` float64 (parity export)."""
         out = torch.empty((self.n, 3), dtype=torch.float64, device=self.starts.device)
@@ -241,6 +268,11 @@ class Operator:
             stream that list -- for retrieval loops that apply one operator hundreds of times
             and have the memory (``op.stored_bytes``).  Same results to the precision of the
             stored lengths (float32 lengths: relative 6e-8 per segment).
+            "packed" stores 4 bytes per segment (3-bit step code + 29-bit length, relative
+            2.4e-7; ``include/sphrt.h``).  "auto" packs as many whole observations as fit in
+            the memory budget (80 % of the free device memory, or ``SPHRT_STORE_BUDGET_GB``)
+            and regenerates the others in every call: the hybrid operator
+            (``op.n_stored_rays`` of ``op._rays.n`` rays come from the list).
     """
 
     def __init__(self, grid, geom, dynamic=False, ftype=FTYPE, itype=ITYPE, device=DEVICE,
@@ -264,8 +296,14 @@ class Operator:
         self._rays = _Rays(geom, self._cdev, self._tables)
         self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         self._stored = None
+        self._packed = None
         self._autotune()
-        if store_segments:
+        if isinstance(store_segments, str):
+            if store_segments not in ("packed", "auto"):
+                raise ValueError(f"store_segments={store_segments!r}: expected False, True, a dtype, "
+                                 "'packed' or 'auto'")
+            self._pack(None if store_segments == "packed" else self._store_budget())
+        elif store_segments:
             self._store(torch.float64 if store_segments is torch.float64 else torch.float32)
         if debug:
             self._print_los(debug_los)
@@ -328,12 +366,106 @@ class Operator:
         self._stored = (offsets, vox, lens)
         self.n_segments = total
 
+    def _store_budget(self):
+        """Bytes the packed list may take: SPHRT_STORE_BUDGET_GB, else 80 % of the free memory."""
+        import os
+        env = os.environ.get("SPHRT_STORE_BUDGET_GB")
+        if env:
+            return int(float(env) * 1e9)
+        free, _ = torch.cuda.mem_get_info(self._cdev)
+        return int(0.8 * free)
+
+    def _pack(self, budget=None):
+        """Pack the segments of the first observations (all of them if ``budget`` is None or they
+        fit) at 4 bytes per segment; the other observations stay regenerated (hybrid operator)."""
+        r, t = self._rays, self._tables
+        count = torch.empty(r.n, dtype=torch.int32, device=self._cdev)
+        scratch = self._scratch()
+        with torch.cuda.device(self._cdev):
+            _cabi.check(self._lib.sphrt_pack_count(t.c, r.c, count.data_ptr(), None,
+                                                   scratch.data_ptr(), scratch.numel(), self._stream()))
+        offsets = torch.zeros(r.n + 1, dtype=torch.int64, device=self._cdev)
+        torch.cumsum(count, 0, out=offsets[1:])
+        del count
+        n_s = r.n
+        if budget is not None:
+            unit = r.unit
+            ends = offsets[unit::unit]                                   # words up to each observation's end
+            cost = 4 * ends + 8 * (torch.arange(1, ends.numel() + 1, device=self._cdev) * unit + 1)
+            n_s = int((cost <= budget).sum().item()) * unit
+        offsets = offsets[:n_s + 1].clone()
+        total = int(offsets[-1].item())
+        words = torch.empty(max(total, 1), dtype=torch.int32, device=self._cdev)
+        if n_s > 0:
+            with torch.cuda.device(self._cdev):
+                _cabi.check(self._lib.sphrt_pack_segments(t.c, r.struct(n_s, r.c.walker), offsets.data_ptr(),
+                                                          words.data_ptr(), scratch.data_ptr(),
+                                                          scratch.numel(), self._stream()))
+        self._packed = (offsets, words, n_s)
+        self._suffix = r.struct_from(n_s, r.c.walker) if n_s < r.n else None
+        self._suffix_scratch_bytes = int(self._lib.sphrt_scratch_bytes(t.c, r.n - n_s)) if n_s < r.n else 0
+
+    @property
+    def n_stored_rays(self):
+        """Rays served from a stored list (the others are regenerated in every call)."""
+        if self._packed is not None:
+            return self._packed[2]
+        return self._rays.n if self._stored is not None else 0
+
     @property
     def stored_bytes(self):
         """Device memory held by the stored segment list (0 when segments are regenerated)."""
+        if self._packed is not None:
+            return sum(t.numel() * t.element_size() for t in self._packed[:2])
         return 0 if self._stored is None else sum(t.numel() * t.element_size() for t in self._stored)
 
+    def _hybrid_call(self, forward, src, dst, n_vol, rays_per_vol):
+        """Packed prefix + regenerated suffix of the ray list.  The C ABI takes dense
+        ``(n_vol, n_rays)`` blocks, so each part works on its own block of the result (forward) or
+        of the weights (adjoint; both parts accumulate into the same gradient)."""
+        offsets, words, n_s = self._packed
+        n, t = self._rays.n, self._tables
+        packed = self._lib.sphrt_forward_packed if forward else self._lib.sphrt_adjoint_packed
+        traced = self._lib.sphrt_forward if forward else self._lib.sphrt_adjoint
+        rays_side = dst if forward else src                 # the tensor indexed by ray
+        if rays_side.dim() == 2 and n_vol == 1:
+            rays_side = rays_side.reshape(-1)
+        flat = rays_side.dim() == 1
+        parts = []
+        with torch.cuda.device(self._cdev):
+            for lo, hi in ((0, n_s), (n_s, n)):
+                if lo == hi:
+                    continue
+                whole = lo == 0 and hi == n
+                if whole:
+                    blk = rays_side
+                elif flat:
+                    blk = rays_side[lo:hi]                      # contiguous slice, used in place
+                else:
+                    blk = torch.empty((n_vol, hi - lo), dtype=rays_side.dtype, device=self._cdev) if forward \
+                        else rays_side[:, lo:hi].contiguous()
+                vol = dst if not forward else src
+                nv = n_vol
+                if rays_per_vol > 0 and lo > 0:                 # observation o reads time-slice o
+                    o0 = lo // rays_per_vol
+                    vol, nv = vol.reshape(n_vol, -1)[o0:], n_vol - o0
+                a, b = (vol, blk) if forward else (blk, vol)
+                if lo == 0:
+                    _cabi.check(packed(offsets.data_ptr(), words.data_ptr(), hi, t.ne, t.na, a.data_ptr(),
+                                       _DTYPES[a.dtype], nv, rays_per_vol, t.nvox, b.data_ptr(), self._stream()))
+                else:
+                    scratch = torch.empty(max(self._suffix_scratch_bytes, 8), dtype=torch.uint8, device=self._cdev)
+                    _cabi.check(traced(t.c, self._suffix, a.data_ptr(), _DTYPES[a.dtype], nv, rays_per_vol,
+                                       b.data_ptr(), scratch.data_ptr(), scratch.numel(), self._stream()))
+                parts.append((lo, hi, blk, whole))
+        if forward and not flat:
+            for lo, hi, blk, whole in parts:
+                if not whole:
+                    dst[:, lo:hi] = blk
+
     def _volume_call(self, forward, src, dst, n_vol, rays_per_vol):
+        if self._packed is not None:
+            return self._hybrid_call(forward, src, dst, n_vol, rays_per_vol)
         if self._stored is not None:
             offsets, vox, lens = self._stored
             fn = self._lib.sphrt_forward_stored if forward else self._lib.sphrt_adjoint_stored

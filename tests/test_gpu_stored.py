@@ -82,3 +82,117 @@ def test_stored_operator_equals_on_the_fly(S):
     ys.sum().backward()
     ref = fly.T(torch.ones(fly._rays.shape, device="cuda"))
     assert torch.allclose(xs.grad[1], ref, rtol=1e-5, atol=1e-5)
+
+
+# ---- packed list (4 bytes per segment) and the hybrid operator -------------------------------------
+
+def _decode_packed(offsets, words, ne, na):
+    """Host restatement of the packed format of include/sphrt.h: per ray (flat voxel offsets, lengths)."""
+    off = offsets.cpu().numpy()
+    w = words.cpu().numpy().view(np.uint32)
+    delta = np.array([1, -1, na, -na, ne * na, -ne * na, 0, 0], dtype=np.int64)
+    rays = []
+    for i in range(len(off) - 1):
+        ww = w[off[i]:off[i + 1]]
+        code, payload = ww >> 29, ww & 0x1FFFFFFF
+        vox, lens, idx = [], [], None
+        for c, p in zip(code.tolist(), payload.tolist()):
+            if c == 7:
+                idx = p
+                continue
+            idx = idx + int(delta[c])
+            vox.append(idx)
+            lens.append(np.array([p << 2], dtype=np.uint32).view(np.float32)[0])
+        rays.append((np.array(vox, dtype=np.int64), np.array(lens, dtype=np.float64)))
+    return rays
+
+
+@pytest.mark.parametrize("name", ["c2_static_rand", "rand_full_inside", "rand_partial", "parallel_hollow"])
+def test_packed_words_decode_to_the_canonical_segments(S, name):
+    c, dens, shape, op = _case_operator(S, name, store_segments="packed")
+    offsets, words, n_s = op._packed
+    assert n_s == op._rays.n and op.n_stored_rays == n_s
+    nr, ne, na = c.nvox
+    vox, lens, count = op.segments()
+    vox = vox.reshape(-1, vox.shape[-2], 3).cpu().numpy().astype(np.int64)
+    lens = lens.reshape(-1, lens.shape[-1]).cpu().numpy()
+    count = count.reshape(-1).cpu().numpy()
+    n_esc = 0
+    for i, (pv, pl) in enumerate(_decode_packed(offsets, words, ne, na)):
+        k = count[i]
+        flat = (vox[i, :k, 0] * ne + vox[i, :k, 1]) * na + vox[i, :k, 2]
+        assert len(pv) == k and np.array_equal(pv, flat), i
+        assert np.allclose(pl, lens[i, :k], rtol=3e-7, atol=1e-30), i
+        n_esc += int(offsets[i + 1] - offsets[i]) - k
+    # one escape per ray that has segments, a few more at seams and holes: the list stays near 4 B/segment
+    assert n_esc < (count > 0).sum() + 0.05 * count.sum() + 8
+
+
+@pytest.mark.parametrize("name", ["c1_rand", "c2_static_rand", "c2_multichannel", "c4_dynamic",
+                                  "rand_full_inside", "rand_partial", "rand_log", "parallel_hollow"])
+def test_packed_operator_matches_reference_golden(S, name):
+    c, dens, shape, op = _case_operator(S, name, store_segments="packed")
+    x = torch.from_numpy(dens).cuda().requires_grad_(True)
+    y = op(x)
+    want = c.integral
+    tol = 1e-5            # BASELINE.json: integrals and gradients within rtol 1e-5 in float32
+    st = np.broadcast_to(c.stable.reshape(shape), want.shape[-len(shape):] if shape else ())
+    st = np.broadcast_to(st, want.shape)
+    got = y.detach().cpu().numpy()
+    assert got.shape == want.shape
+    assert np.allclose(got[st], want[st], rtol=tol, atol=tol), np.abs(got[st] - want[st]).max()
+    if hasattr(c, "grad"):
+        w = case_weights(c)
+        (y * torch.from_numpy(w).cuda()).sum().backward()
+        g = x.grad.cpu().numpy()
+        atol = tol * max(1.0, float(np.abs(c.grad).max()))
+        assert np.allclose(g, c.grad, rtol=10 * tol, atol=atol), np.abs(g - c.grad).max()
+
+
+def _orbit(S, n_obs, shape=(40, 32)):
+    return sum(S.ConeRectGeom(shape, (7 * math.cos(t), 7 * math.sin(t), 1.5 * math.sin(3 * t)), fov=(50, 50))
+               for t in np.linspace(0.2, 5.9, n_obs))
+
+
+@pytest.mark.parametrize("explicit_rays", [False, True])
+def test_hybrid_operator_equals_on_the_fly(S, monkeypatch, explicit_rays):
+    """store_segments='auto' with a budget that holds only some of the observations: the packed
+    prefix and the regenerated rest together give what the regenerated operator gives (static,
+    multi-channel and time-indexed volumes; analytic and uploaded ray directions)."""
+    if explicit_rays:
+        monkeypatch.setenv("SPHRT_RAYGEN", "0")
+    grid = S.SphericalGrid((40, 36, 48), size_r=(0.5, 3))
+    geoms = _orbit(S, 6)
+    fly = S.Operator(grid, geoms)
+    full = S.Operator(grid, geoms, store_segments="packed")
+    assert full.n_stored_rays == fly._rays.n
+    monkeypatch.setenv("SPHRT_STORE_BUDGET_GB", str(0.55 * full.stored_bytes / 1e9))
+    hyb = S.Operator(grid, geoms, store_segments="auto")
+    per_obs = 40 * 32
+    assert 0 < hyb.n_stored_rays < fly._rays.n and hyb.n_stored_rays % per_obs == 0
+    assert hyb.stored_bytes <= 0.55 * full.stored_bytes
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for dt, tol in ((torch.float32, 2e-6), (torch.float64, 2e-6)):
+        x = torch.rand(tuple(grid.shape), generator=gen, device="cuda", dtype=dt)
+        y = torch.rand(fly._rays.shape, generator=gen, device="cuda", dtype=dt)
+        for op in (full, hyb):
+            assert torch.allclose(op(x), fly(x), rtol=tol, atol=tol)
+            assert torch.allclose(op.T(y), fly.T(y), rtol=tol, atol=tol * float(fly.T(y).abs().max()))
+    xs = torch.rand((3,) + tuple(grid.shape), generator=gen, device="cuda").requires_grad_(True)
+    ys = hyb(xs)
+    assert ys.shape == (3,) + fly._rays.shape
+    assert torch.allclose(ys, fly(xs.detach()), rtol=2e-6, atol=2e-6)
+    w = torch.rand(ys.shape, generator=gen, device="cuda")
+    (ys * w).sum().backward()
+    ref = torch.stack([fly.T(w[k]) for k in range(3)])
+    assert torch.allclose(xs.grad, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+    # time-indexed volume: observation o reads time-slice o, in both parts
+    dgrid = S.SphericalGrid((6, 40, 36, 48), size_r=(0.5, 3))
+    dfly = S.Operator(dgrid, geoms)
+    dhyb = S.Operator(dgrid, geoms, store_segments="auto")
+    assert 0 < dhyb.n_stored_rays < dfly._rays.n
+    xd = torch.rand(tuple(dgrid.shape), generator=gen, device="cuda")
+    yd = torch.rand(dfly._rays.shape, generator=gen, device="cuda")
+    assert torch.allclose(dhyb(xd), dfly(xd), rtol=2e-6, atol=2e-6)
+    gd, gr = dhyb.T(yd), dfly.T(yd)
+    assert torch.allclose(gd, gr, rtol=2e-6, atol=2e-6 * float(gr.abs().max()))
