@@ -1565,6 +1565,9 @@ int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in
 // carries the absolute voxel offset, followed by a "stay" word with the length.  The reference
 // stores 32 bytes for each of its K padded slots per ray (raytracer.py:66-72, 675-679).
 constexpr uint32_t kPackLenMask = 0x1fffffffu;
+#ifndef SPHRT_PACK_GROUPS
+#define SPHRT_PACK_GROUPS 2
+#endif
 enum { PACK_STAY = 6, PACK_ESC = 7 };
 
 __host__ __device__ __forceinline__ int pack_code(int d, int na, int nena)
@@ -1708,26 +1711,45 @@ packed_apply_kernel(const int64_t* __restrict__ offsets, const uint32_t* __restr
             } else {
                 vin = in + (v0 + v) * nvox;
             }
+            // The scan carries ONE integer per lane: sum of steps since the last escape, plus 2^30
+            // once an escape is part of it (voxel offsets are below 2^29, so the sum of steps stays
+            // inside (-2^29, 2^29) and the biased value inside [2^30, 2^30 + 2^29)).  The words of
+            // the next group are loaded before the current group's gathers are issued.
+            constexpr int kBias = 1 << 30, kHalf = 1 << 29;
+            constexpr int G = SPHRT_PACK_GROUPS;               // groups of 32 words in flight per warp
+            const uint32_t pad = (uint32_t)PACK_STAY << 29;
             int carry = 0;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                const uint32_t word = k < e ? __ldcs(words + k) : ((uint32_t)PACK_STAY << 29);
-                const uint32_t code = word >> 29, payload = word & kPackLenMask;
-                const bool esc = code == (uint32_t)PACK_ESC;
-                int val = esc ? (int)payload : pack_delta(code, na, nena);
-                int flag = esc ? 1 : 0;
+            uint32_t next[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) { const int64_t k = b + 32 * g + lane; next[g] = k < e ? __ldcs(words + k) : pad; }
+            for (int64_t k0 = b; k0 < e; k0 += 32 * G) {
+                int x[G]; float len[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t word = next[g];
+                    const int64_t kn = k0 + 32 * (G + g) + lane;
+                    next[g] = kn < e ? __ldcs(words + kn) : pad;
+                    const uint32_t code = word >> 29, payload = word & kPackLenMask;
+                    const bool esc = code == (uint32_t)PACK_ESC;
+                    x[g] = esc ? (int)payload + kBias : pack_delta(code, na, nena);
+                    len[g] = esc ? 0.0f : __uint_as_float(payload << 2);
+                }
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int pv = __shfl_up_sync(0xffffffffu, val, o);
-                    const int pf = __shfl_up_sync(0xffffffffu, flag, o);
-                    if (lane >= o && !flag) { val += pv; flag = pf; }
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        const int px = __shfl_up_sync(0xffffffffu, x[g], o);
+                        if (lane >= o && x[g] < kHalf) x[g] += px;
+                    }
                 }
-                const int idx = flag ? val : carry + val;
-                carry = __shfl_sync(0xffffffffu, idx, 31);
-                const float len = esc ? 0.0f : __uint_as_float(payload << 2);
-                if (len != 0.0f) {
-                    if constexpr (kAdjoint) atomicAdd(vout + idx, (T)(w * (double)len));
-                    else acc = fma_rn((double)__ldg(vin + idx), (double)len, acc);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const int idx = x[g] >= kHalf ? x[g] - kBias : carry + x[g];
+                    carry = __shfl_sync(0xffffffffu, idx, 31);
+                    if (len[g] != 0.0f) {
+                        if constexpr (kAdjoint) atomicAdd(vout + idx, (T)(w * (double)len[g]));
+                        else acc = fma_rn((double)__ldg(vin + idx), (double)len[g], acc);
+                    }
                 }
             }
             if constexpr (!kAdjoint) {

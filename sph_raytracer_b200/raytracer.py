@@ -302,7 +302,7 @@ class Operator:
             if store_segments not in ("packed", "auto"):
                 raise ValueError(f"store_segments={store_segments!r}: expected False, True, a dtype, "
                                  "'packed' or 'auto'")
-            self._pack(None if store_segments == "packed" else self._store_budget())
+            self._pack(None if store_segments == "packed" else "auto")
         elif store_segments:
             self._store(torch.float64 if store_segments is torch.float64 else torch.float32)
         if debug:
@@ -367,11 +367,13 @@ class Operator:
         self.n_segments = total
 
     def _store_budget(self):
-        """Bytes the packed list may take: SPHRT_STORE_BUDGET_GB, else 80 % of the free memory."""
+        """Bytes the packed list may take: SPHRT_STORE_BUDGET_GB, else 80 % of the memory that is
+        free (in the driver or cached by torch's allocator) when the list is about to be built."""
         import os
         env = os.environ.get("SPHRT_STORE_BUDGET_GB")
         if env:
             return int(float(env) * 1e9)
+        torch.cuda.empty_cache()
         free, _ = torch.cuda.mem_get_info(self._cdev)
         return int(0.8 * free)
 
@@ -388,12 +390,15 @@ class Operator:
         torch.cumsum(count, 0, out=offsets[1:])
         del count
         n_s = r.n
+        if budget == "auto":
+            budget = self._store_budget() - 8 * (r.n + 1)            # (the offsets are cut out of a copy)
         if budget is not None:
             unit = r.unit
             ends = offsets[unit::unit]                                   # words up to each observation's end
             cost = 4 * ends + 8 * (torch.arange(1, ends.numel() + 1, device=self._cdev) * unit + 1)
             n_s = int((cost <= budget).sum().item()) * unit
-        offsets = offsets[:n_s + 1].clone()
+        if n_s < r.n:
+            offsets = offsets[:n_s + 1].clone()
         total = int(offsets[-1].item())
         words = torch.empty(max(total, 1), dtype=torch.int32, device=self._cdev)
         if n_s > 0:

@@ -18,7 +18,8 @@ def run(spec, reps=7):
     name, _, obs = spec.partition(":")
     grid, geoms, _ = bench.workload(name, int(obs) if obs else None)
     geom = S.ViewGeomCollection(*geoms) if len(geoms) > 1 or grid.dynamic else geoms[0]
-    op = S.Operator(grid, geom, store_segments=bool(os.environ.get('SPHRT_STORE')))
+    store = os.environ.get('SPHRT_STORE')            # 1 (8 B/segment list) | packed | auto
+    op = S.Operator(grid, geom, store_segments=(store if store in ('packed', 'auto') else bool(store)))
     shape = tuple(grid.shape)
     x = torch.rand(shape, device="cuda")
     y = torch.rand(op._rays.shape, device="cuda")
