@@ -314,7 +314,7 @@ def _shard(grid, geoms, rank, world):
     return geom, grid, (lo, hi), f"detector rows over {world} rank(s) ({n_obs} observation(s) < ranks)"
 
 
-def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sampler=None):
+def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sampler=None, store=False):
     """Device-timed forward + adjoint steps of one workload on this rank's shard (max over ranks),
     plus the same step end to end through the public API with host buffers."""
     import torch.distributed as dist
@@ -327,7 +327,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     torch.cuda.reset_peak_memory_stats(dev)
     mem_base = torch.cuda.memory_allocated(dev)        # buffers of the harness itself (L2 flush, ...)
     t0 = time.perf_counter()
-    op = S.Operator(local_grid, geom, device=dev)
+    op = S.Operator(local_grid, geom, device=dev, store_segments=store)
     torch.cuda.synchronize(dev)
     t_build = time.perf_counter() - t0
     n_rays = op._rays.n
@@ -439,13 +439,13 @@ def config_line(m, world):
             "l2": "L2 flushed (256 MB write) between timed steps"}
 
 
-def retrieval_loop(dev, iterations=100):
+def retrieval_loop(dev, iterations=100, store=False):
     """BASELINE configs[2] (examples/static_retrieval.py:18-57): 100 Adam iterations of gd() with
     [SquareLoss, NegRegularizer] through the public API; the REFERENCE's own unchanged gd / loss /
     model classes (baseline/_ref) drive the B200 operator when they are there, else the mirrors."""
     import sph_raytracer_b200 as S
     grid, geoms, _ = workload("c2")
-    op = S.Operator(grid, S.ViewGeomCollection(*geoms), device=dev)
+    op = S.Operator(grid, S.ViewGeomCollection(*geoms), device=dev, store_segments=store)
     x = torch.zeros(tuple(grid.shape), device=dev)
     x[:, 25:, :25] = 1; x[:, :25, 25:] = 1
     with torch.no_grad():
@@ -582,8 +582,22 @@ def run_gpu(args):
             if rank == 0:
                 configs[name] = config_line(cm, world)
             del cm
+            # the same configuration through Operator(store_segments="auto") (all of it fits: the
+            # segments are traced once at construction and streamed from a 4 B/segment list)
+            hm = measure(name, None, steps, 5, world, rank, dev, flush=flush, e2e=False, store="auto")
+            if rank == 0:
+                configs[name]["stored_operator"] = {
+                    "forward_ms": hm["t_fwd"], "adjoint_ms": hm["t_adj"], "ms_per_step": hm["ms"],
+                    "ray_segments_per_s": 2 * hm["tot_seg"] / (hm["ms"] / 1e3),
+                    "operator_build_s": hm["t_build"], "stored_gb": hm["op"].stored_bytes / 1e9,
+                    "stored_fraction_of_rays": hm["op"].n_stored_rays / max(1, hm["op"]._rays.n),
+                    "peak_memory_gb": hm["peak_bytes"] / 1e9}
+            del hm
         if world == 1:
             configs["c3"] = retrieval_loop(dev)
+            st = retrieval_loop(dev, store="auto")
+            configs["c3"]["stored_operator"] = {k: st[k] for k in ("ms_per_iteration", "loss_last",
+                                                                   "gpu_launches_per_iteration")}
 
     if rank == 0:
         ms, e2e_step = m["ms"], m["e2e_ms"]
