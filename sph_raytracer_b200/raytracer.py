@@ -14,6 +14,7 @@ GPU and the result is copied back, so reference-style CPU callers keep working),
 the arithmetic always runs in the CUDA extension; if it is missing, construction fails.
 """
 import math
+import types
 
 import torch
 
@@ -667,14 +668,60 @@ class Operator:
         return vox, lens, count, tuple(stats.tolist())
 
     def _print_los(self, los):
-        """debug=True: segment table of one line of sight (reference raytracer.py:175-225)."""
-        vox, lens, count = self.segments()
-        los = tuple(los) if los is not None else (0,) * len(self._rays.shape)
-        k = int(count[los])
-        print("los:", los, "segments:", k)
-        print("  r   e   a        length")
-        for (r, e, a), l in zip(vox[los][:k].tolist(), lens[los][:k].tolist()):
-            print(f"{r:>3} {e:>3} {a:>3}  {l:12.6f}")
+        """debug=True: the slot table of one line of sight in the reference's format (typ / reg /
+        intlen / dist / ind / neg per sorted candidate, raytracer.py:175-225).  Display only: the
+        candidates come from the CUDA extension (sphrt_candidates: the r_torch / e_torch / a_torch
+        tables), the one ray's sort + forward fill + diff (:131-170) is repeated on the host."""
+        r, t = self._rays, self._tables
+        los = tuple(los) if los is not None else (0,) * len(r.shape)
+        i = 0
+        for k, n in zip(los, r.shape):
+            i = i * n + int(k)
+        x = r.starts[i // r.rays_per_start].reshape(1, 3)
+        d = r.directions(self._lib, self._stream()).reshape(-1, 3)[i].reshape(1, 3)
+        one = _Rays(types.SimpleNamespace(ray_starts=x.cpu(), rays=d.cpu()), self._cdev, t)
+        k1 = 2 * (t.nr + 1) + 2 * (t.ne + 1) + (t.na + 1)
+        ts = torch.empty((1, k1), dtype=torch.float64, device=self._cdev)
+        reg = torch.empty((1, k1), dtype=torch.int32, device=self._cdev)
+        geo = torch.empty((1, k1), dtype=torch.int32, device=self._cdev)
+        with torch.cuda.device(self._cdev):
+            _cabi.check(self._lib.sphrt_candidates(t.c, one.c, ts.data_ptr(), reg.data_ptr(), geo.data_ptr(),
+                                                   self._stream()))
+        ts, reg, geo = ts[0].cpu(), reg[0].cpu().long(), geo[0].cpu().long()
+        nb = (t.nr + 1, t.ne + 1, t.na + 1)
+        kind = torch.cat([torch.full((2 * nb[0],), 0), torch.full((2 * nb[1],), 1), torch.full((nb[2],), 2),
+                          torch.tensor([-1])])
+        ind = torch.cat([torch.arange(nb[0]).repeat(2), torch.arange(nb[1]).repeat(2), torch.arange(nb[2]),
+                         torch.tensor([-1])])
+        neg = torch.cat([ind[:-1] - geo, torch.tensor([-1])])
+        start = one.cells[0, 3:6].cpu().long()                        # find_starts of the start point
+        regs = torch.full((3, k1 + 1), -2, dtype=torch.long)
+        for f in range(3):
+            regs[f, :k1][kind[:-1] == f] = reg[kind[:-1] == f]
+        regs[:, k1] = start
+        ts = torch.cat([ts, torch.zeros(1, dtype=torch.float64)])
+        ts[ts == float("inf")] = float("nan")                       # the table marks "no root" with +inf
+        regs[:, ts < 0] = -2                                          # behind the start (:127)
+        ts_s, order = ts.sort()
+        regs = regs[:, order]
+        state = start.clone()
+        for k in range(k1 + 1):                                       # forward fill (:17-45)
+            upd = regs[:, k] != -2
+            state = torch.where(upd, regs[:, k], state)
+            regs[:, k] = state
+        lens = torch.diff(ts_s, append=torch.tensor([float("inf")], dtype=torch.float64))
+        lens[lens.isinf() | lens.isnan()] = 0
+        shape = torch.tensor([t.nr, t.ne, t.na])[:, None]
+        lens[((regs > shape - 1) | (regs < 0)).any(0)] = 0
+        kmap = {-1: "?", 0: "r", 1: "e", 2: "a"}
+        print("ray_start:", x[0].cpu())
+        print("ray:", d[0].cpu())
+        print("typ   reg       intlen     dist      ind  neg")
+        print("---------------------------------------------")
+        for k in range(k1 + 1):
+            o = int(order[k])
+            print(f"{kmap[int(kind[o])]:<2}", f"r:[{int(regs[0, k]):>2},{int(regs[1, k]):>2},{int(regs[2, k]):>2}]",
+                  f"l:{float(lens[k]):<6.2f}", f"t:{float(ts_s[k]):<10.2f}" f"i:{int(ind[o]):<2}", f"n:{int(neg[o]):<2}")
 
     def plot(self, *args, **kwargs):
         raise NotImplementedError("plotting is outside the scope of the B200 operator")

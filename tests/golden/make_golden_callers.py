@@ -12,7 +12,9 @@ reference on the CPU (build container only; the fixtures are committed):
   grid, 20 x ConeCircGeom (100, 50)): every 7th ray's integral of a seeded volume and the autograd
   gradient of every 13th voxel
 
-    python tests/golden/make_golden_callers.py [retrieval] [preview] [c4]
+* ``debug_los.txt`` -- what ``Operator(..., debug=True, debug_los=(3, 4))`` prints (raytracer.py:175-225)
+
+    python tests/golden/make_golden_callers.py [retrieval] [preview] [c4] [debug]
 """
 import os
 import sys
@@ -98,7 +100,22 @@ def c4():
     print("c4_full:", tuple(y.shape), float(y.sum()))
 
 
+def debug():
+    """The reference's debug printer (raytracer.py:175-225) for one line of sight."""
+    import contextlib
+    import io
+    from sph_raytracer import ConeRectGeom
+    grid = SphericalGrid(shape=(6, 5, 8), size_r=(1, 3))
+    geom = ConeRectGeom((8, 8), pos=(6.0, 1.5, 2.0), fov=(40, 40))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        Operator(grid, geom, debug=True, debug_los=(3, 4))
+    with open(os.path.join(HERE, "debug_los.txt"), "w") as f:
+        f.write(buf.getvalue())
+    print(buf.getvalue()[:600])
+
+
 if __name__ == "__main__":
-    todo = sys.argv[1:] or ["retrieval", "preview", "c4"]
+    todo = sys.argv[1:] or ["retrieval", "preview", "c4", "debug"]
     for name in todo:
-        {"retrieval": retrieval, "preview": preview, "c4": c4}[name]()
+        {"retrieval": retrieval, "preview": preview, "c4": c4, "debug": debug}[name]()

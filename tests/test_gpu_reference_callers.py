@@ -141,3 +141,21 @@ def test_dynamic_measurements_at_full_size_match_the_reference(S, store):
         np.abs(got - z["integral"])[stable].max()
     g = x.grad.reshape(-1)[::13].cpu().numpy()
     assert np.allclose(g, z["grad"], rtol=1e-4, atol=1e-5 * np.abs(z["grad"]).max()), np.abs(g - z["grad"]).max()
+
+
+def test_debug_printer_prints_the_reference_slot_table(S, capsys):
+    """Operator(..., debug=True, debug_los=...) (raytracer.py:175-225): same header and, for every
+    slot that carries a segment, the same row (typ, filled region, length, distance, boundary
+    index, negative-crossing flag) as the reference printed for this line of sight."""
+    want = open(os.path.join(GOLDEN, "debug_los.txt")).read().splitlines()
+    grid = S.SphericalGrid(shape=(6, 5, 8), size_r=(1, 3))
+    geom = S.ConeRectGeom((8, 8), pos=(6.0, 1.5, 2.0), fov=(40, 40))
+    S.Operator(grid, geom, debug=True, debug_los=(3, 4))
+    got = capsys.readouterr().out.splitlines()
+    assert got[2:4] == want[2:4]                                   # column header and rule
+    assert got[0].startswith("ray_start:") and got[1].startswith("ray:")
+    assert len(got) == len(want)                                   # one row per slot (K = candidates + start)
+    rows = lambda lines: [" ".join(l.split()) for l in lines[4:] if "l:0.00" not in l]
+    assert rows(got) == rows(want) and len(rows(want)) > 8
+    # the first slot is the start point, of no family
+    assert got[4].split()[0] == "?" and want[4].split()[0] == "?"
