@@ -174,6 +174,17 @@ struct VolumeMap {
 };
 
 // predicated accumulate / gather of the warp walker's forward sink (see ForwardOp::WSink)
+#ifndef SPHRT_WARP_WARPS
+#define SPHRT_WARP_WARPS 24
+#endif
+#ifndef SPHRT_FWD_WARPS
+#define SPHRT_FWD_WARPS 20
+#endif
+#ifndef SPHRT_FWD_OPAQUE
+#define SPHRT_FWD_OPAQUE true
+#endif
+constexpr int kWarpMaxWarps = SPHRT_WARP_WARPS;      // warps per block of the second-generation warp walker
+
 __device__ __forceinline__ void fma_if(float& acc, float a, float b, unsigned p)
 {
     asm("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q fma.rn.f32 %0, %1, %2, %0;\n}"
@@ -329,7 +340,8 @@ struct ForwardOp {
     }
     int32_t* miss_count() const { return nullptr; }
     // warp-cooperative walker: every lane holds a partial sum of the same ray
-    static constexpr bool kCoop = true, kEvents = false, kOpaqueBases = true;
+    static constexpr bool kCoop = true, kEvents = false, kOpaqueBases = SPHRT_FWD_OPAQUE;
+    static constexpr int kWarpWarps = SPHRT_FWD_WARPS;
     __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
     __device__ __forceinline__ void coop_end(int64_t ray, Sink& s, int lane, int) const
     {
@@ -434,6 +446,7 @@ struct AdjointOp {
     int32_t* miss_count() const { return nullptr; }
     __device__ __forceinline__ void end(int64_t, Sink&) const {}
     static constexpr bool kCoop = true, kEvents = false, kOpaqueBases = false;
+    static constexpr int kWarpWarps = kWarpMaxWarps;
     __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
     // a ray whose weights are all zero (masked measurements: loss.py projection_mask) adds nothing
     __device__ __forceinline__ bool void_ray(int64_t ray) const
@@ -579,6 +592,7 @@ struct EventTraceOp {
     int32_t* miss_count() const { return count; }
     __device__ __forceinline__ void end(int64_t ray, Sink&) const { count[ray] = 0; }   // a miss
     static constexpr bool kCoop = true, kEvents = true, kOpaqueBases = false;
+    static constexpr int kWarpWarps = kWarpMaxWarps;
     __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
     __device__ __forceinline__ void coop_end(int64_t ray, Sink&, int lane, int n_events) const
     {
@@ -921,21 +935,17 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
     }
 }
 
-#ifndef SPHRT_WARP_WARPS
-#define SPHRT_WARP_WARPS 24
-#endif
-constexpr int kWarpMaxWarps = SPHRT_WARP_WARPS;
 constexpr unsigned kWarpBatch = 8;              // records per hand-out
 
 // walk_warp_kernel: persistent warps take batches of planned rays from the dense record list.
 // kAllCones: the list of all-cones records (stored from the back of the buffer: `recs` points at its
 // first record and is walked downwards); failures go to pass B's mask.
+// Op::kWarpWarps: warps per block (= per SM) the kernel is compiled for.  24 warps leave 80
+// registers per thread, 20 leave 96: the forward pass is faster with 20 on large grids (its
+// gathers evict the spill slots from L1, so it pays for every spilled register with an L2 round
+// trip: 9.23 against 9.60 ms per 16 config-5 observations), the adjoint with 24 (8.33 / 8.72).
 template <class Op, bool kAllCones>
-#ifdef SPHRT_WARP_MAXNREG
-__global__ void __maxnreg__(SPHRT_WARP_MAXNREG)
-#else
-__global__ void __launch_bounds__(kWarpMaxWarps * 32, 1)
-#endif
+__global__ void __launch_bounds__(Op::kWarpWarps * 32, 1)
 walk_warp_kernel(sphrt_grid kg, const double* __restrict__ starts, Op op, WarpPlan P,
                  const PlanRec* __restrict__ recs, const unsigned* n_recs_p, int64_t ray_base,
                  uint32_t* mask_back, unsigned* counter, unsigned* n_back, unsigned long long* stats)
@@ -1400,13 +1410,17 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
             op.miss_count(), stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
-        int64_t blocks = (n + (int64_t)wl.P.warps * kWarpBatch - 1) / ((int64_t)wl.P.warps * kWarpBatch);
+        // (the plan's layout holds for fewer warps; their lists are not allocated, which leaves the
+        // SM a larger L1: that, more than the registers, is what the forward pass gains from)
+        const int warps = wl.P.warps < Op::kWarpWarps ? wl.P.warps : Op::kWarpWarps;
+        const size_t smem = wl.smem - (size_t)(wl.P.warps - warps) * wl.P.warp_bytes;
+        int64_t blocks = (n + (int64_t)warps * kWarpBatch - 1) / ((int64_t)warps * kWarpBatch);
         if (blocks > sms) blocks = sms;
-        walk_warp_kernel<Op, false><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
+        walk_warp_kernel<Op, false><<<(unsigned)blocks, warps * 32, smem, cx.st>>>(
             *cx.grid, cx.kr.starts, op, wl.P, cx.recs, wc, base, cx.mask_tracked, wc + 2, wc + 5, stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
-        walk_warp_kernel<Op, true><<<(unsigned)blocks, wl.P.warps * 32, wl.smem, cx.st>>>(
+        walk_warp_kernel<Op, true><<<(unsigned)blocks, warps * 32, smem, cx.st>>>(
             *cx.grid, cx.kr.starts, op, wl.P, cx.recs + (cap - 1), wc + 1, base, cx.mask_listed, wc + 3, wc + 4, stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
