@@ -935,7 +935,10 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
     }
 }
 
-constexpr unsigned kWarpBatch = 8;              // records per hand-out
+#ifndef SPHRT_WARP_BATCH
+#define SPHRT_WARP_BATCH 8
+#endif
+constexpr unsigned kWarpBatch = SPHRT_WARP_BATCH;   // records per hand-out
 
 // walk_warp_kernel: persistent warps take batches of planned rays from the dense record list.
 // kAllCones: the list of all-cones records (stored from the back of the buffer: `recs` points at its
