@@ -1235,6 +1235,7 @@ WarpLaunch plan_warp(const sphrt_grid& g)
     off = ((size_a > size_b ? size_a : size_b) + 15) / 16 * 16;
     P.off_tEA = take((P.capEA + 1) * 8);
     P.off_sEA = take((P.capEA + 2) * 4);
+    P.off_flag = take(8);
     P.warp_bytes = (off + 15) / 16 * 16;
     P.table_doubles = Tab32::doubles(g.nr, g.ne, g.na);        // the walking kernel's own tables
     const int64_t tables = P.table_doubles * (int64_t)sizeof(double);

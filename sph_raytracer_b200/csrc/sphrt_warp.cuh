@@ -45,6 +45,7 @@ struct WarpPlan {
     int off_tE, off_rE, off_tA, off_rA;      // phase A: elevation / azimuth lists
     int off_tR;                              // phase B: radial list, overlays phase A
     int off_tEA, off_sEA;                    // merged elevation + azimuth list
+    int off_flag;                            // two flag words
     int warp_bytes, warps, table_doubles;
 };
 
@@ -135,6 +136,20 @@ struct Tab32 {
     }
 };
 
+// v if lo <= v <= hi and !(side < 0) and !(mag <= eps), else +inf
+__device__ __forceinline__ double select_in_range(double v, double lo, double hi, double side, double mag, double eps)
+{
+    double r;
+    asm("{\n .reg .pred p;\n"
+        " setp.ge.f64 p, %1, %2;\n"
+        " setp.le.and.f64 p, %1, %3, p;\n"
+        " setp.geu.and.f64 p, %4, 0d0000000000000000, p;\n"
+        " setp.gtu.and.f64 p, %5, %6, p;\n"
+        " selp.f64 %0, %1, 0d7FF0000000000000, p;\n}"
+        : "=d"(r) : "d"(v), "d"(lo), "d"(hi), "d"(side), "d"(mag), "d"(eps));
+    return r;
+}
+
 // number of X entries among the first g entries of merge(X, Y), X winning ties; X / Y are the
 // shared addresses of the lists; `steps` bisections (>= log2(min(nX, nY)) + 1, warp-uniform)
 __device__ __forceinline__ int warp_corank(uint32_t X, int nX, uint32_t Y, int nY, int g, int steps)
@@ -190,7 +205,15 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     c.dx = dot3(c.d0, c.d1, c.d2, c.x0, c.x1, c.x2);
     c.xz2 = c.x2 * c.x2;
     c.r0 = c.r1 = c.r2 = 0.0;
-    bool bad = false;
+    // Two per-warp flag words in shared memory instead of per-lane booleans carried through the
+    // loops (the compiler packed those into bytes of one register and spent a dozen instructions
+    // per candidate pass on keeping them): [0] a structural check failed, [1] a glancing crossing
+    // (region "unchanged") is in the elevation list.  Set by predicated stores, read after the loops.
+    const uint32_t flags = wbase + P.off_flag;
+    sts_s32(flags, 0); sts_s32(flags + 4u, 0);
+    __syncwarp();
+#define SPHRT_BAD_IF(cond) do { if (cond) sts_s32(flags, 1); } while (0)
+#define SPHRT_FAILED() (__syncwarp(), __any_sync(SPHRT_FULL, lds_s32(flags) != 0))
     const int na = T.na;
 
     // the chord inside the outermost shell: same expressions as the radial list below
@@ -205,7 +228,7 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     const int e_count = R.e_cs < 0 ? -R.e_cs : R.e_cs, e_step = R.e_cs < 0 ? -1 : 1;
     const int e_mid = R.e_mid;
     int nDown = 0, nUp = 0;
-    bool unchanged = false;
+#define SPHRT_UNCHANGED_IF(cond) do { if (cond) sts_s32(flags + 4u, 1); } while (0)
     if constexpr (kAllCones) {
         // every cone, both roots, unsorted into the (still unused) merge buffers ...
         const uint32_t tmpT = wbase + P.off_tEA, tmpR = wbase + P.off_sEA + 4u;
@@ -227,11 +250,11 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             int geo;
             if (v1) {
                 if (s1 < P.capE) { sts_f64(tmpT + 8u * s1, t1); sts_s32(tmpR + 4u * s1, cone_region_ne(T.ne, c, i, t1, &geo)); }
-                else bad = true;
+                else SPHRT_BAD_IF(true);
             }
             if (v2) {
                 if (s2 < P.capE) { sts_f64(tmpT + 8u * s2, t2); sts_s32(tmpR + 4u * s2, cone_region_ne(T.ne, c, i, t2, &geo)); }
-                else bad = true;
+                else SPHRT_BAD_IF(true);
             }
             n += __popc(m1) + __popc(m2);
         }
@@ -250,9 +273,9 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                 const int reg = lds_s32(tmpR + 4u * e);
                 sts_f64(tEbuf + 8u * rank, te);
                 sts_s32(rEbuf + 4u * rank, reg >= 0 ? reg * na : (reg == -2 ? kUnchangedState : kInvalidState));
-                unchanged |= reg == -2;
+                SPHRT_UNCHANGED_IF(reg == -2);
             }
-        } else bad = true;
+        } else SPHRT_BAD_IF(true);
         nUp = n;
     } else {
         int k = lane, i = R.e_first + lane * e_step;
@@ -276,7 +299,7 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                 int geo;
                 if (ta < SPHRT_INF) ra = cone_region_ne(T.ne, c, i, ta, &geo);
                 // the candidates at both ends of the range are guards: they must stay silent
-                if ((k == 0 || k == e_count - 1) && ta < SPHRT_INF) bad = true;
+                SPHRT_BAD_IF((k == 0 || k == e_count - 1) && ta < SPHRT_INF);
             }
             if (__any_sync(SPHRT_FULL, tb < SPHRT_INF)) {           // cones crossed twice inside the chord
                 int geo;
@@ -285,7 +308,7 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             const bool a_down = ta < R.t_turn;                      // first crossing (towards the turn)
             const bool a_up = ta < SPHRT_INF && !a_down;
             const bool b_up = tb < SPHRT_INF;
-            if (a_up && b_up) bad = true;                           // two crossings after the turn
+            SPHRT_BAD_IF(a_up && b_up);                             // two crossings after the turn
             const uint32_t md = __ballot_sync(SPHRT_FULL, a_down);
             const uint32_t mu = __ballot_sync(SPHRT_FULL, a_up || b_up);
             if (a_down) {
@@ -293,8 +316,8 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                 if (slot >= 0) {
                     sts_f64(tEbuf + 8u * slot, ta);
                     sts_s32(rEbuf + 4u * slot, ra >= 0 ? ra * na : (ra == -2 ? kUnchangedState : kInvalidState));
-                } else bad = true;
-                unchanged |= ra == -2;
+                } else SPHRT_BAD_IF(true);
+                SPHRT_UNCHANGED_IF(ra == -2);
             }
             if (a_up || b_up) {
                 const int slot = e_mid + nUp + __popc(mu & lt_mask);
@@ -302,13 +325,13 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                 if (slot < P.capE) {
                     sts_f64(tEbuf + 8u * slot, a_up ? ta : tb);
                     sts_s32(rEbuf + 4u * slot, rr >= 0 ? rr * na : (rr == -2 ? kUnchangedState : kInvalidState));
-                } else bad = true;
-                unchanged |= rr == -2;
+                } else SPHRT_BAD_IF(true);
+                SPHRT_UNCHANGED_IF(rr == -2);
             }
             nDown += __popc(md); nUp += __popc(mu);
         }
     }
-    if (__any_sync(SPHRT_FULL, bad)) return -1;           // (also keeps the offsets below in range)
+    if (SPHRT_FAILED()) return -1;                        // (also keeps the offsets below in range)
     const uint32_t tE = tEbuf + 8u * (e_mid - nDown), rE = rEbuf + 4u * (e_mid - nDown);
     const int nE = nDown + nUp;
     if (lane == 0) {
@@ -335,6 +358,7 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                 if (pl == 0 || pl == na) {
                     warp_seam_plane(T, c, pl, t_in, t, geo);
                     if (!(t <= t_out)) t = SPHRT_INF;
+                    geo = geo < 0 ? geo + na : (geo >= na ? geo - na : geo);   // full circle
                 } else {
                     // plane_event() with the validity kept in a predicate.  Two exact identities
                     // are used: fma(0, z, y) == y for finite z (the reference's einsum carries the
@@ -345,21 +369,20 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
                     const double num = fma_rn(ca, c.x1, (-sa) * c.x0);
                     const double den = fma_rn(ca, c.d1, (-sa) * c.d0);
                     const double tt = -num / den;
-                    geo = pl - (den < 0 ? 1 : 0);
+                    geo = pl - (den < 0 ? 1 : 0);                    // 1 <= pl < na: already a sector
                     const double px = tt * c.d0 + c.x0, py = tt * c.d1 + c.x1;
-                    const bool valid = !(fabs(den) <= SPHRT_A_PARALLEL) && !(ca * px + sa * py < 0) &&
-                                       tt >= t_in && tt <= t_out;
-                    if (valid) t = tt;
+                    // valid = !(|den| <= 1e-15) && !(ca px + sa py < 0) && t_in <= tt <= t_out, as ONE
+                    // predicate chain (written as C++ the four tests become four pairs of selects)
+                    t = select_in_range(tt, t_in, t_out, ca * px + sa * py, fabs(den), SPHRT_A_PARALLEL);
                 }
-                if (k == a_count - 1 && t < SPHRT_INF) bad = true;     // guard
+                SPHRT_BAD_IF(k == a_count - 1 && t < SPHRT_INF);       // guard
             }
             const bool hit = t < SPHRT_INF;
             const uint32_t mv = __ballot_sync(SPHRT_FULL, hit);
             if (hit) {
                 const int slot = __popc(mv & lt_mask);
-                const int reg = geo < 0 ? geo + na : (geo >= na ? geo - na : geo);   // full circle
                 sts_f64(oT + 8u * slot, t);
-                sts_s32(oR + 4u * slot, reg);
+                sts_s32(oR + 4u * slot, geo);
             }
             const int cnt = __popc(mv);
             nA += cnt; oT += 8u * cnt; oR += 4u * cnt;
@@ -370,11 +393,10 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
         sts_s32(rA - 4u, R.sa0 >= 0 ? R.sa0 : kInvalidState);
     }
     const int nEA = nE + nA;
-    if (nEA > P.capEA) bad = true;
-    if (__any_sync(SPHRT_FULL, bad)) return -1;
-    __syncwarp();
+    if (nEA > P.capEA) return -1;
+    if (SPHRT_FAILED()) return -1;
     // glancing crossings leave the elevation index unchanged: forward-fill (rare)
-    if (__any_sync(SPHRT_FULL, unchanged)) {
+    if (__any_sync(SPHRT_FULL, lds_s32(flags + 4u) != 0)) {
         if (lane == 0) {
 #pragma unroll 1
             for (int k = 0; k < nE; k++)
@@ -451,14 +473,13 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             const double t1c = sqrt(arg);
             // inward roots enter shell i - 1, outward roots shell i; when tangent within rounding
             // the reference decides from the sign of d.p: bail out
-            if (!(arg >= tang + 1e-17 * r2)) bad = true;
+            SPHRT_BAD_IF(!(arg >= tang + 1e-17 * r2));
             sts_f64(lo, c.tc - t1c);
             sts_f64(hi, c.tc + t1c);
         }
         for (int k = lane; k < P.padR; k += 32) sts_f64(tR + 8u * (nR + k), SPHRT_INF);
     }
-    if (__any_sync(SPHRT_FULL, bad)) return -1;
-    __syncwarp();
+    if (SPHRT_FAILED()) return -1;
 
     // ---- stage 2: radial + (elevation, azimuth); every merged event starts one segment that ends
     // at the next event (the reference's sort + forward-fill + diff, raytracer.py:131-151).
@@ -528,6 +549,9 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
         }
 #undef SPHRT_WARP_STEP
     }
+#undef SPHRT_BAD_IF
+#undef SPHRT_UNCHANGED_IF
+#undef SPHRT_FAILED
     return n;
 }
 
