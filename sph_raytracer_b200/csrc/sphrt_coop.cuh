@@ -107,7 +107,12 @@ struct CoopStartCache {
 // kMode: COOP_ORDINARY (hand the all-cones rays over), COOP_ALLCONES (only those), COOP_BOTH.
 enum { COOP_ORDINARY = 0, COOP_ALLCONES = 1, COOP_BOTH = 2 };
 
-template <int kMode>
+// kAllPlanes (second-generation walker only): a ray that passes (nearly) through the Z axis has no
+// monotone azimuth sweep -- every half-plane has its root at the axis, kept or dropped by the last
+// bits of the half-plane test, as in the reference.  Such a ray is walked in all-cones mode with
+// EVERY half-plane evaluated and rank-sorted as well (a_count == 0 in its record) instead of being
+// left to one thread of pass B.
+template <int kMode, bool kAllPlanes = false>
 __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts& c, const double x[3],
                                              const CoopPlan& P, int64_t start_index,
                                              const int32_t* cells, CoopStartCache& cache, CoopRecord& rec)
@@ -156,7 +161,9 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     // a start ON a cone or half-plane makes the reference keep or lose the t ~ 0 crossing by
     // rounding: no shortcut from the geometry of the entry point then, but the all-cones walk from
     // t = 0 applies the reference's own rule (t >= 0) to the reference's own roots
-    const bool all_cones = listed || cache.on_boundary;
+    const double cross = c.x0 * c.d1 - c.x1 * c.d0;
+    const bool near_axis = !(fabs(cross) > 1e-9 * sqrt(c.nx2));                         // (nearly) through the Z axis
+    const bool all_cones = listed || cache.on_boundary || (kAllPlanes && near_axis);
     if (kMode != COOP_BOTH && all_cones != (kMode == COOP_ALLCONES)) return COOP_LISTED;   // the other run's ray
     // innermost shell with a root: first i with r_i^2 - dperp2 >= 0 (same expression as the walk)
     int lo = 0, hi = g.nr;
@@ -214,8 +221,11 @@ __device__ __forceinline__ int coop_plan_ray(const GridView& g, const RayConsts&
     }
 
     // ---- azimuth: monotone rotation, direction = sign of (x x d)_z
-    const double cross = c.x0 * c.d1 - c.x1 * c.d0;
-    if (!(fabs(cross) > 1e-9 * sqrt(c.nx2))) return hand_over;        // (nearly) through the Z axis
+    if (near_axis) {
+        if (!kAllPlanes) return hand_over;
+        rec.a_dir = 1; rec.a_first = 0; rec.a_count = 0;             // every half-plane, rank-sorted
+        return COOP_RAY;
+    }
     const int dir = cross > 0 ? +1 : -1;
     const int s_in = FastAzimuth::to_sector(g, a_bin_in), s_out = FastAzimuth::to_sector(g, qb_a);
     int sweep = (s_out - s_in) * dir;

@@ -896,7 +896,7 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
         start_index = i / kr.rps;
         ray_setup(c, x, d);
         CoopStartCache cache{-1, true, true, 0, 0, 0};
-        cls = coop_plan_ray<COOP_BOTH>(g, c, x, P, start_index, kr.cells, cache, rec);
+        cls = coop_plan_ray<COOP_BOTH, true>(g, c, x, P, start_index, kr.cells, cache, rec);
         if (!table_ok && cls == COOP_RAY) cls = rec.e_mid == 0 ? COOP_LISTED : COOP_TRACKED;
         if (cls == COOP_MISS && miss_count != nullptr) miss_count[i] = 0;
     }
@@ -1222,6 +1222,14 @@ WarpLaunch plan_warp(const sphrt_grid& g)
     P.capA = g.na / 2 + 4;
     // a chord's colatitude varies by less than pi and its azimuth by at most pi
     P.capEA = g.ne + g.na / 2 + 16;
+    // (rays through the Z axis, walked with every half-plane evaluated, can meet more of them: on
+    // grids where that costs little every half-plane gets a slot; elsewhere such a ray overflows
+    // into pass B)
+    if (g.na <= 128 && g.ne <= 128) {
+        P.capA = g.na + 2;                 // every half-plane once
+        P.capE = 2 * (g.ne + 1) + 2;       // every cone twice (such a ray can pass close to the origin)
+        P.capEA = P.capE + P.capA;
+    }
     P.padR = (P.capR + P.capEA + 31) / 32 + 2;
     int off = 0;
     auto take = [&off](int bytes) { const int o = off; off += (bytes + 7) / 8 * 8; return o; };

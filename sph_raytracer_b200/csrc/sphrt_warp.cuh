@@ -28,6 +28,9 @@
 // Rays whose lists fail verification are flagged for the per-thread walker exactly as before.
 #pragma once
 #include "sphrt_coop.cuh"
+#ifdef SPHRT_DEBUG_FAIL
+#include <cstdio>
+#endif
 
 namespace sphrt {
 
@@ -212,7 +215,11 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     const uint32_t flags = wbase + P.off_flag;
     sts_s32(flags, 0); sts_s32(flags + 4u, 0);
     __syncwarp();
+#ifdef SPHRT_DEBUG_FAIL
+#define SPHRT_BAD_IF(cond) do { if (cond) { sts_s32(flags, 1); printf("bad ray %d line %d lane %d\n", R.ray, __LINE__, lane); } } while (0)
+#else
 #define SPHRT_BAD_IF(cond) do { if (cond) sts_s32(flags, 1); } while (0)
+#endif
 #define SPHRT_FAILED() (__syncwarp(), __any_sync(SPHRT_FULL, lds_s32(flags) != 0))
     const int na = T.na;
 
@@ -343,7 +350,52 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     const uint32_t tA = wbase + P.off_tA, rA = wbase + P.off_rA + 4u;
     const int a_count = R.a_cd < 0 ? -R.a_cd : R.a_cd, a_dir = R.a_cd < 0 ? -1 : 1;
     int nA = 0;
-    {
+    bool all_planes = false;
+    if constexpr (kAllCones) all_planes = a_count == 0;
+    if (all_planes) {
+        // every half-plane (both seam planes, as the reference evaluates them), the valid roots
+        // unsorted into the still unused merge buffers, then to their rank (:131; ties in
+        // evaluation order)
+        const uint32_t tmpT = wbase + P.off_tEA, tmpR = wbase + P.off_sEA + 4u;
+        int n = 0;
+#pragma unroll 1
+        for (int i = lane; __any_sync(SPHRT_FULL, i <= na); i += 32) {
+            double t = SPHRT_INF;
+            int reg = 0;
+            if (i <= na) {
+                double ca, sa;
+                lds_f64x2(T.plane + 16u * i, ca, sa);
+                const Event ev = plane_event_v(ca, sa, c, i, na, 1);
+                if (ev.t >= t_in && ev.t <= t_out) t = ev.t;
+                reg = ev.region;
+            }
+            const bool hit = t < SPHRT_INF;
+            const uint32_t mv = __ballot_sync(SPHRT_FULL, hit);
+            const int slot = n + __popc(mv & lt_mask);
+            if (hit) {
+                if (slot < P.capEA) { sts_f64(tmpT + 8u * slot, t); sts_s32(tmpR + 4u * slot, reg); }
+                else SPHRT_BAD_IF(true);
+            }
+            n += __popc(mv);
+        }
+        __syncwarp();
+        if (n <= P.capA && n <= P.capEA) {
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32) {
+                const double te = lds_f64(tmpT + 8u * e);
+                int rank = 0;
+#pragma unroll 1
+                for (int j = 0; j < n; j++) {
+                    const double tj = lds_f64(tmpT + 8u * j);
+                    rank += (tj < te || (tj == te && j < e)) ? 1 : 0;
+                }
+                sts_f64(tA + 8u * rank, te);
+                sts_s32(rA + 4u * rank, lds_s32(tmpR + 4u * e));
+            }
+        } else SPHRT_BAD_IF(true);
+        nA = n;
+        __syncwarp();
+    } else {
         int k = lane, pl0 = R.a_first + lane * a_dir;
         const int pl_step = 32 * a_dir;
         uint32_t oT = tA, oR = rA;
@@ -393,7 +445,12 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
         sts_s32(rA - 4u, R.sa0 >= 0 ? R.sa0 : kInvalidState);
     }
     const int nEA = nE + nA;
-    if (nEA > P.capEA) return -1;
+    if (nEA > P.capEA) {
+#ifdef SPHRT_DEBUG_FAIL
+        if (lane == 0) printf("capEA ray %d nE %d nA %d\n", R.ray, nE, nA);
+#endif
+        return -1;
+    }
     if (SPHRT_FAILED()) return -1;
     // glancing crossings leave the elevation index unchanged: forward-fill (rare)
     if (__any_sync(SPHRT_FULL, lds_s32(flags + 4u) != 0)) {
@@ -454,7 +511,12 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             sts_f64(tEA + 8u * nEA, SPHRT_INF);
             sts_s32(sEA - 4u, lds_s32(rE - 4u) + lds_s32(rA - 4u) + base_r);
         }
-        if (__any_sync(SPHRT_FULL, viol)) return -1;
+        if (__any_sync(SPHRT_FULL, viol)) {
+#ifdef SPHRT_DEBUG_FAIL
+            if (viol) printf("viol ray %d lane %d nE %d nA %d allp %d\n", R.ray, lane, nE, nA, (int)all_planes);
+#endif
+            return -1;
+        }
     }
     __syncwarp();                                      // phase A lists are dead from here on
 
@@ -472,8 +534,10 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             const double arg = r2 - c.dperp2;
             const double t1c = sqrt(arg);
             // inward roots enter shell i - 1, outward roots shell i; when tangent within rounding
-            // the reference decides from the sign of d.p: bail out
-            SPHRT_BAD_IF(!(arg >= tang + 1e-17 * r2));
+            // the reference decides from the sign of d.p: bail out.  (Not for an innermost "shell" of
+            // radius 0 met by a ray through the origin: both roots are tc, the reference gives both
+            // region 0, here the ray is below the grid for a length of exactly zero in between.)
+            SPHRT_BAD_IF(!(arg >= tang + 1e-17 * r2) && r2 != 0.0);
             sts_f64(lo, c.tc - t1c);
             sts_f64(hi, c.tc + t1c);
         }
