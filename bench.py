@@ -314,7 +314,8 @@ def _shard(grid, geoms, rank, world):
     return geom, grid, (lo, hi), f"detector rows over {world} rank(s) ({n_obs} observation(s) < ranks)"
 
 
-def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sampler=None, store=False):
+def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sampler=None, store=False,
+            fused=False):
     """Device-timed forward + adjoint steps of one workload on this rank's shard (max over ranks),
     plus the same step end to end through the public API with host buffers."""
     import torch.distributed as dist
@@ -376,6 +377,26 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     else:
         ms = float(np.mean([a.elapsed_time(d) for a, b, c, d in evs]))
 
+    # the fused normal-equations step (Operator.normal: A x and A^T (w * (A x - b)) in one walk), timed
+    # like the two passes above -- an extension for retrieval loops, reported next to the headline
+    t_fused = None
+    if fused:
+        def fused_step():
+            _, gg = op.normal(x, b=y, scale=0.5)
+            if reduce_grad:
+                dist.all_reduce(gg)
+        for _ in range(min(warmup, 2)):
+            fused_step()
+        barrier()
+        fe = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(2)) for _ in range(steps)]
+        for k in range(steps):
+            if flush is not None:
+                flush()
+            fe[k][0].record(); fused_step(); fe[k][1].record()
+        barrier()
+        t_fused = float(np.mean([a.elapsed_time(b) for a, b in fe])) if flush is not None else \
+            fe[0][0].elapsed_time(fe[-1][1]) / steps
+
     # end to end through the public API: host buffers in, host buffers out, autograd adjoint;
     # the upload of the adjoint input rides a copy stream under the forward pass, the download of
     # the integrals under the adjoint pass
@@ -412,16 +433,18 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     peak_bytes = torch.cuda.max_memory_allocated(dev) - mem_base
     clocks = sampler.summary() if sampler is not None else None
 
-    stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
+                         dtype=torch.float64, device=dev)
     sums = torch.tensor([float(n_seg), float(n_rays)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, t_fwd, t_adj, peak_bytes, t_build = stats.tolist()
+    ms, e2e_ms, t_fwd, t_adj, peak_bytes, t_build, t_fused = stats.tolist()
     tot_seg, tot_rays = sums.tolist()
     return {"op": op, "grid": grid, "local_grid": local_grid, "desc": desc, "sharding": sharding, "dynamic": dynamic,
             "ms": ms, "e2e_ms": e2e_ms if e2e else None, "t_fwd": t_fwd, "t_adj": t_adj, "peak_bytes": peak_bytes,
-            "t_build": t_build, "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
+            "t_build": t_build, "t_fused": t_fused if fused else None,
+            "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
             "launches": launches, "x": x, "y": y, "out": out, "vshape": vshape, "block": (lo, hi), "clocks": clocks,
             "h2d": x_host.numel() * 4 + y_host.numel() * 4, "d2h": out_host.numel() * 4 + grad_host.numel() * 4}
 
@@ -439,7 +462,7 @@ def config_line(m, world):
             "l2": "L2 flushed (256 MB write) between timed steps"}
 
 
-def retrieval_loop(dev, iterations=100, store=False):
+def retrieval_loop(dev, iterations=100, store=False, fused=False):
     """BASELINE configs[2] (examples/static_retrieval.py:18-57): 100 Adam iterations of gd() with
     [SquareLoss, NegRegularizer] through the public API; the REFERENCE's own unchanged gd / loss /
     model classes (baseline/_ref) drive the B200 operator when they are there, else the mirrors."""
@@ -461,6 +484,9 @@ def retrieval_loop(dev, iterations=100, store=False):
         from sph_raytracer_b200.loss import SquareLoss, NegRegularizer
         from sph_raytracer_b200.model import FullyDenseModel
         who = "mirrored gd/loss/model"
+    if fused:       # this package's drop-in loss class, inside whichever gd() drives the loop
+        from sph_raytracer_b200.loss import FusedSquareLoss as SquareLoss
+        who += " + FusedSquareLoss (one walk per iteration)"
     model = FullyDenseModel(grid)
     gd(op, y, model, lr=1e-1, loss_fns=[SquareLoss(), NegRegularizer()], num_iterations=3, progress_bar=False)
     torch.cuda.synchronize(dev)
@@ -490,7 +516,8 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    m = measure(args.workload, args.obs, args.steps, args.warmup, world, rank, dev, sampler=ClockSampler(local))
+    m = measure(args.workload, args.obs, args.steps, args.warmup, world, rank, dev, sampler=ClockSampler(local),
+                fused=True)
     clocks = m["clocks"]
     op, grid, dynamic = m["op"], m["grid"], m["dynamic"]
 
@@ -577,10 +604,11 @@ def run_gpu(args):
         flush = _Flush(dev)
         for name in ("c1", "c2", "c4"):
             steps = 20
-            cm = measure(name, None, steps, 5, world, rank, dev, flush=flush)
+            cm = measure(name, None, steps, 5, world, rank, dev, flush=flush, fused=True)
             cm["steps"] = steps
             if rank == 0:
                 configs[name] = config_line(cm, world)
+                configs[name]["fused_normal_step_ms"] = cm["t_fused"]
             del cm
             # the same configuration through Operator(store_segments="auto") (all of it fits: the
             # segments are traced once at construction and streamed from a 4 B/segment list)
@@ -598,6 +626,9 @@ def run_gpu(args):
             st = retrieval_loop(dev, store="auto")
             configs["c3"]["stored_operator"] = {k: st[k] for k in ("ms_per_iteration", "loss_last",
                                                                    "gpu_launches_per_iteration")}
+            fu = retrieval_loop(dev, fused=True)
+            configs["c3"]["fused_square_loss"] = {k: fu[k] for k in ("driver", "ms_per_iteration", "loss_last",
+                                                                     "gpu_launches_per_iteration")}
 
     if rank == 0:
         ms, e2e_step = m["ms"], m["e2e_ms"]
@@ -648,6 +679,9 @@ def run_gpu(args):
             # counted by the library itself (sphrt_launch_count): every kernel it launched in the timed steps
             "gpu_launches": int(m["launches"]),
             "walker": op.walker(),
+            # how that kernel was chosen: timed against the per-thread walker once per problem shape at
+            # construction (Operator._autotune; part of operator_build_s), reused afterwards
+            "autotune": getattr(op, "autotune", None),
             "clocks": clocks,
             "peak_memory_gb": m["peak_bytes"] / 1e9,
             # what the reference keeps for the same rays (regs + lens, raytracer.py:17-45) and its own
@@ -679,6 +713,13 @@ def run_gpu(args):
                 "peak_source": "tools/microbench/peaks.cu on this GPU model (profiles/r1c_secondary_peaks.json)"}
         except Exception:
             pass
+        if m["t_fused"]:
+            line["fused_normal_step"] = {
+                "ms_per_step": m["t_fused"], "speedup_vs_two_passes": ms / m["t_fused"],
+                "equivalent_ray_segments_per_s": 2 * tot_seg / (m["t_fused"] / 1e3),
+                "note": "Operator.normal(x, b): A x and A^T (w * (A x - b)) in ONE walk of the rays (what a "
+                        "SquareLoss + autograd iteration needs), gradient all-reduced like the adjoint's; an "
+                        "extension for retrieval loops, not the headline value"}
         if stored is not None:
             line["stored_operator"] = stored
         if configs is not None:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 5
+#define SPHRT_VERSION 6
 
 enum {
     SPHRT_OK = 0,
@@ -138,6 +138,18 @@ int sphrt_count_segments(const sphrt_grid *grid, const sphrt_rays *rays,
 int sphrt_trace_segments(const sphrt_grid *grid, const sphrt_rays *rays, int64_t max_seg,
                          int32_t *vox, double *seg_len, int32_t *count,
                          void *scratch, int64_t scratch_bytes, void *stream);
+
+/* Fused normal-equations step (extension for retrieval loops; the reference spends one forward and
+ * one adjoint trace per iteration on SquareLoss + autograd, loss.py:86-90, retrieval.py:99-116):
+ *     out  = A x                                  (n_rays)
+ *     grad += A^T (scale * mask * (A x - b))      (n_vol, nr, ne, na); the caller zero-fills grad
+ * in ONE walk of the rays.  b and mask are (n_rays) arrays of the volume's dtype and may be NULL
+ * (b = 0, mask = 1).  One volume per ray: n_vol = 1, or rays_per_vol > 0 (time-indexed volume, as in
+ * sphrt_forward).  Returns SPHRT_EINVAL for grids the warp-cooperative walker does not serve
+ * (sphrt_walker_kind); the caller then runs sphrt_forward and sphrt_adjoint. */
+int sphrt_normal(const sphrt_grid *grid, const sphrt_rays *rays, const void *density, int dtype,
+                 int64_t n_vol, int64_t rays_per_vol, void *out, const void *b, const void *mask,
+                 double scale, void *grad, void *scratch, int64_t scratch_bytes, void *stream);
 
 /* Stored operator (optional).  The reference precomputes and stores its operator
  * (Operator.regs / .lens, raytracer.py:675-679: 32 bytes for each of K padded slots per ray) and

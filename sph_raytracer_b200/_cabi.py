@@ -17,7 +17,8 @@ EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphr
            "sphrt_find_starts", "sphrt_trace_events", "sphrt_walker_kind",
            "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates",
            "sphrt_launch_count", "sphrt_export_rays",
-           "sphrt_pack_count", "sphrt_pack_segments", "sphrt_forward_packed", "sphrt_adjoint_packed")
+           "sphrt_pack_count", "sphrt_pack_segments", "sphrt_forward_packed", "sphrt_adjoint_packed",
+           "sphrt_normal")
 
 
 class Grid(ctypes.Structure):
@@ -96,6 +97,9 @@ def load(path=None):
     lib.sphrt_forward_packed.argtypes = packed_args
     lib.sphrt_adjoint_packed.restype = c_int
     lib.sphrt_adjoint_packed.argtypes = packed_args
+    lib.sphrt_normal.restype = c_int
+    lib.sphrt_normal.argtypes = [P(Grid), P(Rays), c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p,
+                                 c_void_p, ctypes.c_double, c_void_p, c_void_p, c_int64, c_void_p]
     lib.sphrt_candidates.restype = c_int
     lib.sphrt_candidates.argtypes = [P(Grid), P(Rays), c_void_p, c_void_p, c_void_p, c_void_p]
     lib.sphrt_walker_kind.restype = c_int

@@ -2,7 +2,7 @@
 
 The shared library sits next to this file so that it travels with the source tree
 (``gpurun`` snapshots) and is never installed into site-packages.  The three translation units
-(forward kernels, adjoint kernels, everything else) are compiled in parallel and linked.
+(forward kernels, adjoint kernels, the fused normal step, everything else) are compiled in parallel and linked.
 """
 import os
 import shutil
@@ -11,7 +11,7 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = [os.path.join(CSRC, n) for n in ("sphrt_forward.cu", "sphrt_adjoint.cu", "sphrt_api.cu")]
+SOURCES = [os.path.join(CSRC, n) for n in ("sphrt_forward.cu", "sphrt_adjoint.cu", "sphrt_api.cu", "sphrt_normal.cu")]
 HEADERS = [os.path.join(CSRC, n) for n in ("sphrt_kernels.cuh", "sphrt_walker.cuh", "sphrt_fast.cuh",
                                            "sphrt_coop.cuh", "sphrt_warp.cuh")] + [os.path.join(HERE, "..", "include", "sphrt.h")]
 LIB = os.path.join(HERE, "libsphrt.so")

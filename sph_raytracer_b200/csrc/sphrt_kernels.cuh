@@ -279,6 +279,7 @@ struct ForwardOp {
     // sums in float32, raytracer.py:710-713), the 32 partial sums are added in float64.  Wider
     // batches accumulate directly in float64.
     struct WSink {
+        static constexpr bool kTwoSweeps = false;
         const T* vol; int nvox; int nch;
         double acc[NCH];
         T facc, pv[kWarpDepth], pl[kWarpDepth]; unsigned pk[kWarpDepth];
@@ -413,6 +414,7 @@ struct AdjointOp {
         return s;
     }
     struct WSink {
+        static constexpr bool kTwoSweeps = false;
         T* vol; int nvox; int nch;
         double w[NCH];
         template <int SLOT>
@@ -459,6 +461,100 @@ struct AdjointOp {
             if (c < nch) zero &= __ldg(y + (int64_t)(ch0 + c) * m.n_rays + ray) == T(0);
         return zero;
     }
+};
+
+// Fused normal-equations step for retrieval loops (an extension, not a path of the reference:
+// SquareLoss + autograd there cost one forward and one adjoint walk per iteration,
+// loss.py:86-90, retrieval.py:99-116): out = A x and grad += A^T (scale * mask * (A x - b)) in ONE
+// walk of the warp walker.  The weight of a ray's back-projection depends only on that ray's own
+// integral, and after the forward sweep its merged lists are still in shared memory: the second
+// sweep repeats the segment loop only (~15 % of a walk).  One volume per ray (static, or the
+// time-slice of its observation).
+template <typename T>
+struct NormalOp {
+    const T* density; T* out; const T* b; const T* mask; double scale; T* grad; VolumeMap m;
+    // second sweep: the adjoint sink with the weight just computed
+    struct WSink2 {
+        static constexpr bool kTwoSweeps = false;
+        bool active; T* vol; double w;
+        template <int SLOT>
+        __device__ __forceinline__ void seg(bool ok, unsigned idx, double len)
+        {
+            red_add_global_if(ok, vol + idx, (T)(w * len));
+        }
+    };
+    struct WSink {
+        static constexpr bool kTwoSweeps = true;
+        T* out; const T* b; const T* mask; double scale; T* grad; int64_t ray, vol_index, nvox;
+        const T* vol;
+        T facc, pv[kWarpDepth], pl[kWarpDepth]; unsigned pk[kWarpDepth];
+        template <int SLOT>
+        __device__ __forceinline__ void seg(bool ok, unsigned idx, double len)
+        {
+            fma_if(facc, pv[SLOT], pl[SLOT], pk[SLOT]);
+            pk[SLOT] = ok ? 1u : 0u; pl[SLOT] = (T)len;
+            ldg_if(pv[SLOT], vol, idx, pk[SLOT]);
+        }
+        __device__ __forceinline__ WSink2 second(int lane)
+        {
+#pragma unroll
+            for (int k = 0; k < kWarpDepth; k++) fma_if(facc, pv[k], pl[k], pk[k]);
+            double a = (double)facc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            const T y = (T)a;                          // the integral as the forward pass stores it
+            if (lane == 0) out[ray] = y;
+            double w = scale * ((double)y - (b != nullptr ? (double)__ldg(b + ray) : 0.0));
+            if (mask != nullptr) w *= (double)__ldg(mask + ray);
+            return WSink2{w != 0.0, grad + vol_index * nvox, w};
+        }
+    };
+    __device__ __forceinline__ WSink wbegin(int64_t ray) const
+    {
+        WSink s;
+        s.out = out; s.b = b; s.mask = mask; s.scale = scale; s.grad = grad;
+        s.ray = ray; s.vol_index = m.first_volume(ray, 0); s.nvox = m.nvox;
+        s.vol = density + s.vol_index * m.nvox;
+        s.facc = T(0);
+#pragma unroll
+        for (int k = 0; k < kWarpDepth; k++) { s.pk[k] = 0u; s.pl[k] = T(0); s.pv[k] = T(0); }
+        return s;
+    }
+    __device__ __forceinline__ void wend(int64_t, WSink&, int, int) const {}
+    // rays that never reach the grid: integral 0 (their weight scatters nowhere)
+    int prefill(cudaStream_t st) const { return (int)cudaMemsetAsync(out, 0, sizeof(T) * (size_t)m.n_rays, st); }
+    int32_t* miss_count() const { return nullptr; }
+    static constexpr bool kCoop = true, kEvents = false, kOpaqueBases = true;
+    static constexpr int kWarpWarps = SPHRT_FWD_WARPS;
+    __device__ __forceinline__ bool void_ray(int64_t) const { return false; }
+    // (the per-thread fallback passes run as a forward and an adjoint launch: launch_normal)
+    struct Sink { static constexpr int kDepth = 1; };
+};
+
+// adjoint of the fused step for the rays the fallback passes walk: the weight comes from the
+// integral the forward fallback launch has just stored
+template <typename T>
+struct NormalAdjointOp {
+    const T* out; const T* b; const T* mask; double scale; T* grad; VolumeMap m;
+    using Sink = typename AdjointOp<T, 1>::Sink;
+    __device__ __forceinline__ double weight(int64_t ray) const
+    {
+        double w = scale * ((double)__ldg(out + ray) - (b != nullptr ? (double)__ldg(b + ray) : 0.0));
+        if (mask != nullptr) w *= (double)__ldg(mask + ray);
+        return w;
+    }
+    __device__ __forceinline__ Sink begin(int64_t ray) const
+    {
+        Sink s;
+        s.vol = grad + m.first_volume(ray, 0) * m.nvox;
+        s.nvox = (int)m.nvox; s.ne = m.ne; s.na = m.na; s.nch = 1;
+        s.w[0] = weight(ray);
+        return s;
+    }
+    __device__ __forceinline__ void end(int64_t, Sink&) const {}
+    static constexpr bool kCoop = false, kEvents = false;
+    __device__ __forceinline__ bool void_ray(int64_t ray) const { return weight(ray) == 0.0; }
+    __device__ __forceinline__ void coop_end(int64_t, Sink&, int, int) const {}
 };
 
 // canonical segment bookkeeping shared by count / trace: consecutive identical voxels merge
@@ -567,6 +663,7 @@ struct EventTraceOp {
         return Sink{vox + 3 * ray * max_ev, ev_len + ray * max_ev, max_ev};
     }
     struct WSink {
+        static constexpr bool kTwoSweeps = false;
         int32_t* vox; double* len; int64_t max_ev; int nr;
         template <int SLOT>
         __device__ __forceinline__ void seg(bool, unsigned, double) {}
@@ -1441,8 +1538,10 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
 }
 
 template <class Op>
-int launch_tracked_masked(const PassContext& cx, const Op& op, const unsigned* n_work = nullptr)
+int launch_tracked_masked(const PassContext& cx, const Op& op, const unsigned* n_work = nullptr,
+                          unsigned long long* chunk_counter = nullptr)
 {
+    if (chunk_counter == nullptr) chunk_counter = cx.counters + 1;
     const size_t smem = cx.smem_tables + kQueueBytes;
     if (smem > 40 * 1024)   // (+ the static flag queue)
         cudaFuncSetAttribute(walk_tracked_masked_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1452,7 +1551,7 @@ int launch_tracked_masked(const PassContext& cx, const Op& op, const unsigned* n
     if (blocks < 1) blocks = 1;
     walk_tracked_masked_kernel<Op><<<(unsigned)blocks, kBlock, smem, cx.st>>>(
         *cx.grid, cx.kr, op, (int)(cx.smem_tables / sizeof(double)), cx.mask_tracked, cx.n_words,
-        cx.counters + 1, n_work);
+        chunk_counter, n_work);
     return cuda_status();
 }
 
@@ -1577,6 +1676,52 @@ int launch_volume_op(const sphrt_grid* grid, const sphrt_rays* rays, const T* in
         }
     }
     return SPHRT_OK;
+}
+
+// Fused normal-equations step: plan + warp walk with two sweeps for the cooperative rays; the rays
+// left to the per-thread walkers get a forward and then an adjoint launch of the two fallback
+// passes (both return at once when the planner counted none).  SPHRT_EINVAL if the grid is not
+// served by the second-generation warp walker (the caller then runs the two passes apart).
+template <typename T>
+int launch_normal(const sphrt_grid* grid, const sphrt_rays* rays, const T* density, int64_t n_vol,
+                  int64_t rays_per_vol, T* out, const T* b, const T* mask, double scale, T* grad,
+                  void* scratch, int64_t scratch_bytes, void* stream)
+{
+    if (rays->n_rays == 0) return SPHRT_OK;
+    if (scratch_bytes < sphrt_scratch_bytes(grid, rays->n_rays) || scratch == nullptr) return SPHRT_ESCRATCH;
+    const WarpLaunch wl = plan_warp(*grid);
+    if (!wl.ok || !plan_coop(*grid, rays->n_rays).ok) return SPHRT_EINVAL;
+    VolumeMap m;
+    m.n_rays = rays->n_rays; m.nvox = (int64_t)grid->nr * grid->ne * grid->na;
+    m.n_vol = n_vol; m.rays_per_vol = rays_per_vol; m.ne = grid->ne; m.na = grid->na;
+    PassContext cx;
+    cx.grid = grid;
+    cx.kr = make_krays(rays);
+    cx.st = (cudaStream_t)stream;
+    cx.smem_tables = (size_t)table_doubles(*grid) * sizeof(double);
+    cx.mask_listed = (uint32_t*)scratch;
+    cx.mask_tracked = (uint32_t*)((char*)scratch + mask_bytes(rays->n_rays));
+    cx.counters = (unsigned long long*)((char*)scratch + 2 * mask_bytes(rays->n_rays));
+    cx.lists = (char*)scratch + 2 * mask_bytes(rays->n_rays) + 256;
+    cx.n_words = (rays->n_rays + 31) / 32;
+    cx.recs = reinterpret_cast<PlanRec*>((char*)scratch + scratch_bytes_before_recs(grid, rays->n_rays));
+    cudaMemsetAsync(cx.counters, 0, 8 * sizeof(unsigned long long), cx.st);
+    const ListPlan lp = plan_lists(*grid, rays->n_rays);
+    const unsigned* wc = reinterpret_cast<unsigned*>(cx.counters + 8);
+    const NormalOp<T> op{density, out, b, mask, scale, grad, m};
+    int rc = launch_warp(cx, wl, op, nullptr);
+    if (rc != SPHRT_OK) return rc;
+    // what the warp walker left: integrals first ...
+    const ForwardOp<T, 1> fwd{density, out, m, 0};
+    rc = launch_tracked_masked(cx, fwd, wc + 5);
+    if (rc != SPHRT_OK) return rc;
+    rc = launch_listed(grid, cx.kr, fwd, cx.mask_listed, cx.lists, cx.smem_tables, lp, cx.counters + 2, cx.st, wc + 4);
+    if (rc != SPHRT_OK) return rc;
+    // ... then their back-projection, weighted by the integrals just stored
+    const NormalAdjointOp<T> adj{out, b, mask, scale, grad, m};
+    rc = launch_tracked_masked(cx, adj, wc + 5, cx.counters + 4);
+    if (rc != SPHRT_OK) return rc;
+    return launch_listed(grid, cx.kr, adj, cx.mask_listed, cx.lists, cx.smem_tables, lp, cx.counters + 5, cx.st, wc + 4);
 }
 
 // ---- stored operator: apply passes ---------------------------------------------------------------

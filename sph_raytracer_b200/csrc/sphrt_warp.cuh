@@ -562,6 +562,11 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
         const int gs = g0 < n ? g0 : n;
         const int nmin = nR < nEA ? nR : nEA;
         const int i0 = warp_corank(tR, nR, tEA, nEA, gs, 32 - __clz(nmin > 0 ? nmin : 1));
+        // One sweep over this lane's share of the merged sequence.  A sink may ask for a second
+        // one (Sink::kTwoSweeps: the fused normal-equations step scatters A^T of a weight that
+        // depends on the ray's own integral): the lists are still in shared memory, only the
+        // segment loop is repeated.
+        auto sweep = [&](auto& sink) {
         int u = i0 - m;
         const uint32_t cR = tR + 8u * m;               // radial head: cR + 8 u
         uint32_t cE = tEA + 8u * (gs - m);             // other head after k steps: cE + 8 k - 8 u
@@ -612,6 +617,12 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
             if (q < c2) SPHRT_WARP_STEP(0, 0)
         }
 #undef SPHRT_WARP_STEP
+        };
+        sweep(sink);
+        if constexpr (Sink::kTwoSweeps) {
+            auto second = sink.second(lane);
+            if (second.active) sweep(second);
+        }
     }
 #undef SPHRT_BAD_IF
 #undef SPHRT_UNCHANGED_IF

@@ -31,6 +31,15 @@ def run(spec, reps=7):
         torch.cuda.synchronize()
         if k >= 2:
             tf.append(a.elapsed_time(b)); ta.append(b.elapsed_time(c))
+    if os.environ.get('SPHRT_NORMAL'):           # the fused normal-equations step next to fwd + adj
+        tn = []
+        for k in range(reps + 2):
+            a, b = ev(), ev()
+            a.record(); op.normal(x, b=y, scale=0.5); b.record()
+            torch.cuda.synchronize()
+            if k >= 2:
+                tn.append(a.elapsed_time(b))
+        print(f"{'':40s} {spec:8s} fused normal step {np.median(tn):8.3f} ms (min {min(tn):.3f})  vs fwd + adj {np.median(tf) + np.median(ta):.3f} ms")
     _, nseg = op.segment_counts()
     mode = os.environ.get('SPHRT_LIB', 'default') + (' stored %.2f GB' % (op.stored_bytes / 1e9) if op.stored_bytes else '')
     print(f"{mode:40s} {spec:8s} fwd {np.median(tf):8.3f} ms (min {min(tf):.3f})  "
