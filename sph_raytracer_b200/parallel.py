@@ -150,6 +150,26 @@ class ShardedOperator:
     def __call__(self, density):
         return _ShardedIntegral.apply(density, self)
 
+    def normal(self, density, b=None, mask=None, scale=1.0):
+        """Fused normal-equations step of the local observations (``Operator.normal``): the local
+        integrals and the GLOBAL (all-reduced) ``A^T (scale * mask * (A x - b))``; ``b`` and ``mask``
+        are this rank's blocks.  ``loss.FusedSquareLoss`` finds it through ``hasattr(f, "normal")``."""
+        with torch.no_grad():
+            d = density[self.lo:self.hi] if self.dynamic else density
+            if hasattr(self.local, "normal"):
+                y, g = self.local.normal(d, b=b, mask=mask, scale=scale)
+            else:
+                y = self.local(d)
+                w = y if b is None else y - b
+                if mask is not None:
+                    w = w * mask
+                g = self.local.T(w * scale)
+            if self.dynamic:
+                full = torch.zeros(tuple(density.shape), dtype=g.dtype, device=g.device)
+                full[self.lo:self.hi] = g
+                g = full
+            return y, allreduce_gradient(g.contiguous(), self.group)
+
     def T(self, line_integrations):
         g = self.local.T(line_integrations)
         if self.dynamic:

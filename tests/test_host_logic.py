@@ -143,7 +143,19 @@ def _worker(rank, world, port, q):
     y = sop(x)
     w = torch.ones_like(y) * (rank + 1)
     (y * w).sum().backward()
-    q.put((rank, sop.lo, sop.hi, y.detach().numpy(), x.grad.numpy(), sop.T(w).numpy()))
+    # fused normal step through the sharded operator (dense stand-in: the two-pass form) and the
+    # drop-in loss that uses it: same value and GLOBAL gradient as SquareLoss
+    from sph_raytracer_b200 import loss as L
+    b = torch.full_like(y.detach(), 0.25)
+    yn, gn = sop.normal(x.detach(), b=b, scale=0.5)
+    vals = []
+    for cls in (L.SquareLoss, L.FusedSquareLoss):
+        xx = x.detach().clone().requires_grad_(True)
+        v = cls()(sop, b, xx, None)
+        v.backward()
+        vals.append((float(v), xx.grad.numpy()))
+    q.put((rank, sop.lo, sop.hi, y.detach().numpy(), x.grad.numpy(), sop.T(w).numpy(),
+           yn.numpy(), gn.numpy(), vals))
     dist.destroy_process_group()
 
 
@@ -166,10 +178,13 @@ def test_sharded_operator_gloo_world2():
     w_full = torch.cat([torch.ones(12) * 1, torch.ones(12) * 2]).double()
     grad = (A.T @ w_full).reshape(2, 3, 4).numpy()
     assert [(r[1], r[2]) for r in res] == [(0, 2), (2, 4)]
-    for rank, lo, hi, y, gx, ty in res:
+    gnorm = (A.T @ (0.5 * (A @ x - 0.25))).reshape(2, 3, 4).numpy()
+    for rank, lo, hi, y, gx, ty, yn, gn, vals in res:
         assert np.allclose(y, full[lo:hi])
         assert np.allclose(gx, grad)       # gradient is global (all-reduced) on every rank
         assert np.allclose(ty, grad)
+        assert np.allclose(yn, full[lo:hi]) and np.allclose(gn, gnorm)
+        assert np.isclose(vals[0][0], vals[1][0]) and np.allclose(vals[0][1], vals[1][1])
 
 
 class _DynOp:
