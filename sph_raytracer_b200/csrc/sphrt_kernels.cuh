@@ -206,6 +206,9 @@ __device__ __forceinline__ void ldg_if(double& v, const double* base, unsigned i
                  " @q ld.global.nc.f64 %0, [a];\n}" : "+d"(v) : "l"(base), "r"(idx), "r"(p));
 }
 
+__device__ __forceinline__ float fmaf_or_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fmaf_or_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
 template <typename T, int NCH>
 struct ForwardOp {
     const T* density; T* out; VolumeMap m; int ch0;
@@ -1867,17 +1870,29 @@ packed_apply_kernel(const int64_t* __restrict__ offsets, const uint32_t* __restr
 {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < n_rays; ray += warps) {
-        const int64_t b = __ldg(offsets + ray), e = __ldg(offsets + ray + 1);
-        if (b == e && kAdjoint) continue;
+    // (the warp's ray index is broadcast from lane 0: that is what tells the compiler that the loops
+    // below are warp-uniform -- without it every shuffle of the scan is wrapped in a convergence
+    // barrier and the kernel, L2-bound by design, becomes instruction-bound)
+    const int64_t first = __shfl_sync(0xffffffffu, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, 0);
+    const bool l1 = lane >= 1, l2 = lane >= 2, l4 = lane >= 4, l8 = lane >= 8, l16 = lane >= 16;
+    for (int64_t ray = first; ray < n_rays; ray += warps) {
+        const int64_t b = __ldg(offsets + ray);
+        const int cnt = (int)(__ldg(offsets + ray + 1) - b);
+        if (cnt == 0 && kAdjoint) continue;
+        const uint32_t* __restrict__ wp = words + b;
         const int64_t v0 = rays_per_vol > 0 ? (ray / rays_per_vol) % n_vol : 0;
-        const int64_t nv = rays_per_vol > 0 ? 1 : n_vol;          // channels share the list
-        for (int64_t v = 0; v < nv; v++) {
-            double w = 0.0, acc = 0.0;
+        const int nv = rays_per_vol > 0 ? 1 : (int)n_vol;         // channels share the list
+        for (int v = 0; v < nv; v++) {
+            float w = 0.0f;
+            // per-lane partial sums in the volume's precision (ten-odd terms per lane, as in the
+            // walker's forward sink), added over the warp in float64
+            T acc = T(0);
             const T* vin = nullptr; T* vout = nullptr;
+            double wd = 0.0;
             if constexpr (kAdjoint) {
-                w = (double)__ldg(in + (rays_per_vol > 0 ? ray : v * n_rays + ray));
-                if (w == 0.0) continue;
+                wd = (double)__ldg(in + (rays_per_vol > 0 ? ray : (int64_t)v * n_rays + ray));
+                if (wd == 0.0) continue;
+                w = (float)wd;
                 vout = out + (v0 + v) * nvox;
             } else {
                 vin = in + (v0 + v) * nvox;
@@ -1885,48 +1900,54 @@ packed_apply_kernel(const int64_t* __restrict__ offsets, const uint32_t* __restr
             // The scan carries ONE integer per lane: sum of steps since the last escape, plus 2^30
             // once an escape is part of it (voxel offsets are below 2^29, so the sum of steps stays
             // inside (-2^29, 2^29) and the biased value inside [2^30, 2^30 + 2^29)).  The words of
-            // the next group are loaded before the current group's gathers are issued.
+            // the next groups are loaded before the current groups' gathers are issued.
             constexpr int kBias = 1 << 30, kHalf = 1 << 29;
             constexpr int G = SPHRT_PACK_GROUPS;               // groups of 32 words in flight per warp
             const uint32_t pad = (uint32_t)PACK_STAY << 29;
             int carry = 0;
             uint32_t next[G];
 #pragma unroll
-            for (int g = 0; g < G; g++) { const int64_t k = b + 32 * g + lane; next[g] = k < e ? __ldcs(words + k) : pad; }
-            for (int64_t k0 = b; k0 < e; k0 += 32 * G) {
+            for (int g = 0; g < G; g++) { const int k = 32 * g + lane; next[g] = k < cnt ? __ldcs(wp + k) : pad; }
+            for (int k0 = 0; k0 < cnt; k0 += 32 * G) {
                 int x[G]; float len[G];
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const uint32_t word = next[g];
-                    const int64_t kn = k0 + 32 * (G + g) + lane;
-                    next[g] = kn < e ? __ldcs(words + kn) : pad;
+                    const int kn = k0 + 32 * (G + g) + lane;
+                    next[g] = kn < cnt ? __ldcs(wp + kn) : pad;
                     const uint32_t code = word >> 29, payload = word & kPackLenMask;
                     const bool esc = code == (uint32_t)PACK_ESC;
                     x[g] = esc ? (int)payload + kBias : pack_delta(code, na, nena);
                     len[g] = esc ? 0.0f : __uint_as_float(payload << 2);
                 }
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        const int px = __shfl_up_sync(0xffffffffu, x[g], o);
-                        if (lane >= o && x[g] < kHalf) x[g] += px;
-                    }
+#define SPHRT_SCAN_STEP(O, P)                                                                      \
+                _Pragma("unroll")                                                                  \
+                for (int g = 0; g < G; g++) {                                                      \
+                    const int px = __shfl_up_sync(0xffffffffu, x[g], O);                           \
+                    if (P && x[g] < kHalf) x[g] += px;                                             \
                 }
+                SPHRT_SCAN_STEP(1, l1) SPHRT_SCAN_STEP(2, l2) SPHRT_SCAN_STEP(4, l4)
+                SPHRT_SCAN_STEP(8, l8) SPHRT_SCAN_STEP(16, l16)
+#undef SPHRT_SCAN_STEP
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const int idx = x[g] >= kHalf ? x[g] - kBias : carry + x[g];
                     carry = __shfl_sync(0xffffffffu, idx, 31);
                     if (len[g] != 0.0f) {
-                        if constexpr (kAdjoint) atomicAdd(vout + idx, (T)(w * (double)len[g]));
-                        else acc = fma_rn((double)__ldg(vin + idx), (double)len[g], acc);
+                        if constexpr (kAdjoint) {
+                            if constexpr (sizeof(T) == 4) atomicAdd(vout + idx, (T)(w * len[g]));
+                            else atomicAdd(vout + idx, (T)(wd * (double)len[g]));
+                        } else {
+                            acc = fmaf_or_fma(__ldg(vin + idx), (T)len[g], acc);
+                        }
                     }
                 }
             }
             if constexpr (!kAdjoint) {
+                double a = (double)acc;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) out[rays_per_vol > 0 ? ray : v * n_rays + ray] = (T)acc;
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) out[rays_per_vol > 0 ? ray : (int64_t)v * n_rays + ray] = (T)a;
             }
         }
     }
