@@ -455,7 +455,7 @@ class Operator:
         flat = rays_side.dim() == 1
         parts = []
         with torch.cuda.device(self._cdev):
-            for lo, hi in ((0, n_s), (n_s, n)):
+            for stored_part, lo, hi in ((True, 0, n_s), (False, n_s, n)):
                 if lo == hi:
                     continue
                 whole = lo == 0 and hi == n
@@ -472,7 +472,7 @@ class Operator:
                     o0 = lo // rays_per_vol
                     vol, nv = vol.reshape(n_vol, -1)[o0:], n_vol - o0
                 a, b = (vol, blk) if forward else (blk, vol)
-                if lo == 0:
+                if stored_part:
                     _cabi.check(packed(offsets.data_ptr(), words.data_ptr(), hi, t.ne, t.na, a.data_ptr(),
                                        _DTYPES[a.dtype], nv, rays_per_vol, t.nvox, b.data_ptr(), self._stream()))
                 else:

@@ -178,6 +178,13 @@ def test_hybrid_operator_equals_on_the_fly(S, monkeypatch, explicit_rays):
         for op in (full, hyb):
             assert torch.allclose(op(x), fly(x), rtol=tol, atol=tol)
             assert torch.allclose(op.T(y), fly.T(y), rtol=tol, atol=tol * float(fly.T(y).abs().max()))
+    # a budget that holds nothing: everything regenerated, same numbers
+    monkeypatch.setenv("SPHRT_STORE_BUDGET_GB", "1e-9")
+    none = S.Operator(grid, geoms, store_segments="auto")
+    assert none.n_stored_rays == 0
+    x = torch.rand(tuple(grid.shape), generator=gen, device="cuda")
+    assert torch.equal(none(x), fly(x))
+    monkeypatch.setenv("SPHRT_STORE_BUDGET_GB", str(0.55 * full.stored_bytes / 1e9))
     xs = torch.rand((3,) + tuple(grid.shape), generator=gen, device="cuda").requires_grad_(True)
     ys = hyb(xs)
     assert ys.shape == (3,) + fly._rays.shape
