@@ -431,6 +431,16 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
     peak_bytes = torch.cuda.max_memory_allocated(dev) - mem_base
+    # what of that peak is the operator's own: its persistent state (grid tables, detector frames or
+    # ray directions, start cells, a stored list if any) and the scratch of one call (ray masks,
+    # counters, the warp walker's records of one chunk); the rest are the caller's volumes,
+    # integrals and gradients of the step (forward + adjoint + end-to-end copies)
+    r = op._rays
+    state = sum(t.numel() * t.element_size() for t in (r.starts, r.dirs, r.cells) if t is not None)
+    if r._gen is not None:
+        state += sum(v.numel() * v.element_size() for v in r._gen.values() if isinstance(v, torch.Tensor))
+    state += (op._tables.nr + op._tables.ne + op._tables.na) * 8 * 8 + op.stored_bytes
+    op_bytes = float(state + op._scratch_bytes)
     clocks = sampler.summary() if sampler is not None else None
 
     stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
@@ -443,7 +453,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     tot_seg, tot_rays = sums.tolist()
     return {"op": op, "grid": grid, "local_grid": local_grid, "desc": desc, "sharding": sharding, "dynamic": dynamic,
             "ms": ms, "e2e_ms": e2e_ms if e2e else None, "t_fwd": t_fwd, "t_adj": t_adj, "peak_bytes": peak_bytes,
-            "t_build": t_build, "t_fused": t_fused if fused else None,
+            "t_build": t_build, "t_fused": t_fused if fused else None, "op_bytes": op_bytes,
             "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
             "launches": launches, "x": x, "y": y, "out": out, "vshape": vshape, "block": (lo, hi), "clocks": clocks,
             "h2d": x_host.numel() * 4 + y_host.numel() * 4, "d2h": out_host.numel() * 4 + grad_host.numel() * 4}
@@ -456,6 +466,7 @@ def config_line(m, world):
             "forward_ms": m["t_fwd"], "adjoint_ms": m["t_adj"], "ms_per_step": ms,
             "ray_segments_per_s": 2 * m["tot_seg"] / (ms / 1e3), "rays_per_s": 2 * m["tot_rays"] / (ms / 1e3),
             "e2e_ms_per_step": m["e2e_ms"], "peak_memory_gb": m["peak_bytes"] / 1e9,
+            "operator_memory_gb": m["op_bytes"] / 1e9,
             "reference_memory_gb": reference_memory_gb(m["grid"], m["tot_rays"]),
             "operator_build_s": m["t_build"], "sharding": m["sharding"], "walker": m["op"].walker(),
             "gpu_launches_per_step": m["launches"] / max(1, m.get("steps", 1)),
@@ -684,6 +695,9 @@ def run_gpu(args):
             "autotune": getattr(op, "autotune", None),
             "clocks": clocks,
             "peak_memory_gb": m["peak_bytes"] / 1e9,
+            # the operator's own part of it (state + scratch of one call; rank 0), the rest being the
+            # step's volumes, integrals and gradients incl. the end-to-end copies
+            "operator_memory_gb": m["op_bytes"] / 1e9,
             # what the reference keeps for the same rays (regs + lens, raytracer.py:17-45) and its own
             # working-set estimator (examples/memory_usage.py:23-44), whole job
             "reference_memory_gb": reference_memory_gb(grid, tot_rays),
