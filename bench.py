@@ -439,7 +439,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     state = sum(t.numel() * t.element_size() for t in (r.starts, r.dirs, r.cells) if t is not None)
     if r._gen is not None:
         state += sum(v.numel() * v.element_size() for v in r._gen.values() if isinstance(v, torch.Tensor))
-    state += (op._tables.nr + op._tables.ne + op._tables.na) * 8 * 8 + op.stored_bytes
+    state += (op._tables.nr + op._tables.ne + op._tables.na) * 8 * 8 + op.stored_bytes + op.plan_cache_bytes
     op_bytes = float(state + op._scratch_bytes)
     clocks = sampler.summary() if sampler is not None else None
 

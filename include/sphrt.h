@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPHRT_VERSION 6
+#define SPHRT_VERSION 7
 
 enum {
     SPHRT_OK = 0,
@@ -98,7 +98,21 @@ typedef struct sphrt_rays {
     const float *gen_ta;       /* (gen_h) rows, or (n_obs, gen_h) if gen_per_obs_tables          */
     const float *gen_tb;       /* (gen_w) columns, or (n_obs, gen_w)                             */
     const float *gen_tc;       /* polar detectors only                                           */
+    /* Optional plan cache (sphrt_forward / sphrt_adjoint / sphrt_normal, warp-cooperative walker
+     * only): the per-ray records the planning kernel writes for the walking kernel -- direction,
+     * radial constants, candidate ranges, 80 bytes for every ray that reaches the grid -- and its
+     * two bits per ray are the same in every call on the same rays.  With a caller-owned buffer of
+     * sphrt_plan_cache_bytes() bytes the first call (plan_cache_state 1) keeps them and the
+     * following ones (plan_cache_state 2) skip the planning kernel (~5 % of a pass).  NULL / 0:
+     * planned in every call, in the scratch buffer.  The buffer belongs to one (grid, rays) pair
+     * and to one value of SPHRT_WARP_CHUNK. */
+    void *plan_cache;
+    int64_t plan_cache_bytes;
+    int64_t plan_cache_state;
 } sphrt_rays;
+
+/* Bytes of a plan cache for these rays (0: this grid is not served by the kernels that use one). */
+int64_t sphrt_plan_cache_bytes(const sphrt_grid *grid, int64_t n_rays);
 
 /* Bytes of caller-owned scratch the tracing entry points need for this grid and ray count:
  * two bits per ray (the rays that run in the equatorial plane or pass close to the origin

@@ -18,7 +18,7 @@ EXPORTS = ("sphrt_version", "sphrt_error_string", "sphrt_last_cuda_error", "sphr
            "sphrt_store_segments", "sphrt_forward_stored", "sphrt_adjoint_stored", "sphrt_candidates",
            "sphrt_launch_count", "sphrt_export_rays",
            "sphrt_pack_count", "sphrt_pack_segments", "sphrt_forward_packed", "sphrt_adjoint_packed",
-           "sphrt_normal")
+           "sphrt_normal", "sphrt_plan_cache_bytes")
 
 
 class Grid(ctypes.Structure):
@@ -34,7 +34,8 @@ class Rays(ctypes.Structure):
                 ("dirs", c_void_p), ("rays_per_dir", c_int64), ("start_cells", c_void_p),
                 ("walker", c_int64),
                 ("gen_kind", c_int32), ("gen_h", c_int32), ("gen_w", c_int32), ("gen_per_obs_tables", c_int32),
-                ("gen_frames", c_void_p), ("gen_ta", c_void_p), ("gen_tb", c_void_p), ("gen_tc", c_void_p)]
+                ("gen_frames", c_void_p), ("gen_ta", c_void_p), ("gen_tb", c_void_p), ("gen_tc", c_void_p),
+                ("plan_cache", c_void_p), ("plan_cache_bytes", c_int64), ("plan_cache_state", c_int64)]
 
 
 class SphrtError(RuntimeError):
@@ -65,6 +66,8 @@ def load(path=None):
     lib.sphrt_launch_count.argtypes = []
     lib.sphrt_scratch_bytes.restype = c_int64
     lib.sphrt_scratch_bytes.argtypes = [P(Grid), c_int64]
+    lib.sphrt_plan_cache_bytes.restype = c_int64
+    lib.sphrt_plan_cache_bytes.argtypes = [P(Grid), c_int64]
     vol_args = [P(Grid), P(Rays), c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
     lib.sphrt_forward.restype = c_int
     lib.sphrt_forward.argtypes = vol_args

@@ -36,6 +36,13 @@ int64_t sphrt_scratch_bytes(const sphrt_grid* grid, int64_t n_rays)
 
 
 
+int64_t sphrt_plan_cache_bytes(const sphrt_grid* grid, int64_t n_rays)
+{
+    if (check_grid(grid) != SPHRT_OK || n_rays <= 0) return 0;
+    if (!plan_warp(*grid).ok || !plan_coop(*grid, n_rays).ok) return 0;
+    return plan_cache_layout(n_rays).bytes;
+}
+
 int sphrt_count_segments(const sphrt_grid* grid, const sphrt_rays* rays, int32_t* count,
                          unsigned long long* total, void* scratch, int64_t scratch_bytes, void* stream)
 {

@@ -975,6 +975,7 @@ constexpr int kPlanBlock = 256;
 __global__ void __launch_bounds__(kPlanBlock)
 plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, PlanRec* recs,
                  unsigned* n_recs /* [0] ordinary rays, from the front; [1] all-cones rays, from the back */,
+                 unsigned* n_fallback /* [0] rays left for pass B, [1] for the per-thread walker */,
                  int64_t cap, uint32_t* mask_listed, uint32_t* mask_tracked, int32_t* miss_count,
                  unsigned long long* stats)
 {
@@ -1011,8 +1012,8 @@ plan_warp_kernel(sphrt_grid kg, KRays kr, int64_t base, int64_t n, CoopPlan P, P
         mask_tracked[i >> 5] = m_tracked;
         if (m_ray) slot0 = atomicAdd(n_recs, (unsigned)__popc(m_ray));
         if (m_all) slot1 = atomicAdd(n_recs + 1, (unsigned)__popc(m_all));
-        if (m_listed) atomicAdd(n_recs + 4, (unsigned)__popc(m_listed));      // work of the fallback passes
-        if (m_tracked) atomicAdd(n_recs + 5, (unsigned)__popc(m_tracked));
+        if (m_listed) atomicAdd(n_fallback, (unsigned)__popc(m_listed));      // work of the fallback passes
+        if (m_tracked) atomicAdd(n_fallback + 1, (unsigned)__popc(m_tracked));
         if (stats != nullptr) {
             if (m_listed) atomicAdd(stats + 1, (unsigned long long)__popc(m_listed));
             if (m_tracked) atomicAdd(stats + 2, (unsigned long long)__popc(m_tracked));
@@ -1481,7 +1482,41 @@ struct PassContext {
     void* lists;                         // global cone lists of pass B (very large grids only)
     int64_t n_words;
     PlanRec* recs;                       // records of the second-generation warp walker (one chunk)
+    // plan cache (sphrt_rays.plan_cache): every chunk's records and counts kept between calls
+    PlanRec* cache_recs = nullptr;       // chunk c at cache_recs + c * chunk
+    unsigned* cache_counts = nullptr;    // 8 unsigned per chunk: [0] ordinary, [1] all-cones records
+    unsigned* cache_totals = nullptr;    // [0], [1]: rays of the two fallback passes
+    int cache_state = 0;                 // 1: fill, 2: use
 };
+
+// Layout of a plan cache: [256 B totals][32 B per chunk][listed mask][tracked mask][records]
+struct PlanCacheLayout { int64_t n_chunks, off_counts, off_masks, off_recs, bytes; };
+inline PlanCacheLayout plan_cache_layout(int64_t n_rays)
+{
+    PlanCacheLayout L;
+    const int64_t chunk = warp_chunk_rays();
+    L.n_chunks = (n_rays + chunk - 1) / chunk;
+    L.off_counts = 256;
+    L.off_masks = (L.off_counts + 32 * L.n_chunks + 255) / 256 * 256;
+    L.off_recs = L.off_masks + 2 * mask_bytes(n_rays);
+    L.bytes = L.off_recs + L.n_chunks * (chunk + 32) * (int64_t)sizeof(PlanRec);     // chunk c at c * (chunk + 32)
+    return L;
+}
+
+// Point the pass at the caller's plan cache, if there is one that fits (masks, records, counts).
+inline void attach_plan_cache(PassContext& cx, const sphrt_rays* rays)
+{
+    if (rays->plan_cache == nullptr || rays->plan_cache_state < 1 || rays->plan_cache_state > 2) return;
+    const PlanCacheLayout L = plan_cache_layout(rays->n_rays);
+    if (rays->plan_cache_bytes < L.bytes) return;
+    char* c = (char*)rays->plan_cache;
+    cx.cache_totals = (unsigned*)c;
+    cx.cache_counts = (unsigned*)(c + L.off_counts);
+    cx.mask_listed = (uint32_t*)(c + L.off_masks);
+    cx.mask_tracked = (uint32_t*)(c + L.off_masks + mask_bytes(rays->n_rays));
+    cx.cache_recs = (PlanRec*)(c + L.off_recs);
+    cx.cache_state = (int)rays->plan_cache_state;
+}
 
 template <class Op, int kMode>
 int launch_coop(const PassContext& cx, const CoopLaunch& cl, const Op& op, const uint32_t* in_mask,
@@ -1512,16 +1547,28 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
     const int64_t chunk = warp_chunk_rays();
     const int sms = num_sms();
     cudaMemsetAsync(wc, 0, 8 * sizeof(unsigned), cx.st);
-    for (int64_t base = 0; base < cx.kr.n; base += chunk) {
+    // With a plan cache every chunk has its own record area and counts; the first call (state 1)
+    // fills them, the later ones (state 2) skip the planning kernel.  Events are never cached.
+    const bool cached = cx.cache_recs != nullptr && !Op::kEvents;
+    const bool plan_now = !cached || cx.cache_state == 1;
+    if (cached && !plan_now)        // the planner's counts of the rays left to the fallback passes
+        cudaMemcpyAsync(wc + 4, cx.cache_totals, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, cx.st);
+    int64_t c = 0;
+    for (int64_t base = 0; base < cx.kr.n; base += chunk, c++) {
         const int64_t n = cx.kr.n - base < chunk ? cx.kr.n - base : chunk;
         const int64_t cap = (n + 31) / 32 * 32;
-        if (base > 0) cudaMemsetAsync(wc, 0, 4 * sizeof(unsigned), cx.st);
-        const int64_t pb = (n + kPlanBlock - 1) / kPlanBlock;
-        plan_warp_kernel<<<(unsigned)pb, kPlanBlock, smem_plan, cx.st>>>(
-            *cx.grid, cx.kr, base, n, wl.caps, cx.recs, wc, cap, cx.mask_listed, cx.mask_tracked,
-            op.miss_count(), stats);
-        rc = cuda_status();
-        if (rc != SPHRT_OK) return rc;
+        PlanRec* recs = cached ? cx.cache_recs + c * (chunk + 32) : cx.recs;
+        unsigned* cnt = cached ? cx.cache_counts + 8 * c : wc;          // [0] ordinary, [1] all-cones records
+        if (base > 0 || cached) cudaMemsetAsync(wc, 0, 4 * sizeof(unsigned), cx.st);
+        if (plan_now) {
+            if (cached) cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned), cx.st);
+            const int64_t pb = (n + kPlanBlock - 1) / kPlanBlock;
+            plan_warp_kernel<<<(unsigned)pb, kPlanBlock, smem_plan, cx.st>>>(
+                *cx.grid, cx.kr, base, n, wl.caps, recs, cnt, wc + 4, cap, cx.mask_listed, cx.mask_tracked,
+                op.miss_count(), stats);
+            rc = cuda_status();
+            if (rc != SPHRT_OK) return rc;
+        }
         // (the plan's layout holds for fewer warps; their lists are not allocated, which leaves the
         // SM a larger L1: that, more than the registers, is what the forward pass gains from)
         const int warps = wl.P.warps < Op::kWarpWarps ? wl.P.warps : Op::kWarpWarps;
@@ -1529,14 +1576,16 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
         int64_t blocks = (n + (int64_t)warps * kWarpBatch - 1) / ((int64_t)warps * kWarpBatch);
         if (blocks > sms) blocks = sms;
         walk_warp_kernel<Op, false><<<(unsigned)blocks, warps * 32, smem, cx.st>>>(
-            *cx.grid, cx.kr.starts, op, wl.P, cx.recs, wc, base, cx.mask_tracked, wc + 2, wc + 5, stats);
+            *cx.grid, cx.kr.starts, op, wl.P, recs, cnt, base, cx.mask_tracked, wc + 2, wc + 5, stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
         walk_warp_kernel<Op, true><<<(unsigned)blocks, warps * 32, smem, cx.st>>>(
-            *cx.grid, cx.kr.starts, op, wl.P, cx.recs + (cap - 1), wc + 1, base, cx.mask_listed, wc + 3, wc + 4, stats);
+            *cx.grid, cx.kr.starts, op, wl.P, recs + (cap - 1), cnt + 1, base, cx.mask_listed, wc + 3, wc + 4, stats);
         rc = cuda_status();
         if (rc != SPHRT_OK) return rc;
     }
+    if (cached && plan_now)         // (taken after the walks: a superset of the planner's counts)
+        cudaMemcpyAsync(cx.cache_totals, wc + 4, 2 * sizeof(unsigned), cudaMemcpyDeviceToDevice, cx.st);
     return SPHRT_OK;
 }
 
@@ -1609,6 +1658,7 @@ int launch_passes(const sphrt_grid* grid, const sphrt_rays* rays, const Op& op,
                 wc = reinterpret_cast<unsigned*>(cx.counters + 8);
                 // ordinary rays: plan + walk kernels of sphrt_warp.cuh; then the all-cones rays,
                 // in place on their mask
+                if constexpr (!Op::kEvents) attach_plan_cache(cx, rays);
                 rc = launch_warp(cx, wl, op, stats);
             } else if (rays->n_rays < coop_split_rays()) {
                 rc = launch_coop<Op, COOP_BOTH>(cx, cl, op, nullptr, cx.counters, stats);
@@ -1712,6 +1762,7 @@ int launch_normal(const sphrt_grid* grid, const sphrt_rays* rays, const T* densi
     const ListPlan lp = plan_lists(*grid, rays->n_rays);
     const unsigned* wc = reinterpret_cast<unsigned*>(cx.counters + 8);
     const NormalOp<T> op{density, out, b, mask, scale, grad, m};
+    attach_plan_cache(cx, rays);
     int rc = launch_warp(cx, wl, op, nullptr);
     if (rc != SPHRT_OK) return rc;
     // what the warp walker left: integrals first ...

@@ -301,6 +301,9 @@ class Operator:
         self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         self._stored = None
         self._packed = None
+        self._plan_cache = None          # None: not decided yet; False: not used; else the buffer
+        self._plan_key = None
+        self._plan_pending = None
         self._autotune()
         if isinstance(store_segments, str):
             if store_segments not in ("packed", "auto"):
@@ -485,6 +488,40 @@ class Operator:
                 if not whole:
                     dst[:, lo:hi] = blk
 
+    def _plan_cache_begin(self):
+        """Plan cache of the warp walker (``sphrt_rays.plan_cache``): the planner's 80-byte record per
+        ray and its two bits per ray are the same in every call, so they are kept after the first
+        one if that costs less than 15 % of the free device memory (SPHRT_PLAN_CACHE=0: never).
+        Returns the state to restore after the call."""
+        import os
+        if self._plan_cache is False or os.environ.get("SPHRT_PLAN_CACHE", "1") == "0":
+            self._rays.c.plan_cache_state = 0
+            return
+        key = tuple(os.environ.get(k) for k in ("SPHRT_WARP_CHUNK", "SPHRT_WALKER", "SPHRT_COOP_GEN", "SPHRT_AUTOTUNE"))
+        if self._plan_cache is None:
+            nbytes = int(self._lib.sphrt_plan_cache_bytes(self._tables.c, self._rays.n))
+            if nbytes == 0 or self.walker() != "cooperative" or \
+                    nbytes > 0.15 * torch.cuda.mem_get_info(self._cdev)[0]:
+                self._plan_cache = False
+                return
+            self._plan_cache = torch.empty(nbytes, dtype=torch.uint8, device=self._cdev)
+            self._rays.c.plan_cache = self._plan_cache.data_ptr()
+            self._rays.c.plan_cache_bytes = nbytes
+            self._plan_key = None
+        if key != self._plan_key:            # first call, or the environment picked another kernel path
+            self._plan_pending = key         # (becomes the cache's key once the call has succeeded)
+            self._rays.c.plan_cache_state = 1
+        else:
+            self._rays.c.plan_cache_state = 2
+
+    def _plan_cache_end(self):
+        if getattr(self, "_plan_pending", None) is not None:
+            self._plan_key, self._plan_pending = self._plan_pending, None
+
+    @property
+    def plan_cache_bytes(self):
+        return self._plan_cache.numel() if isinstance(self._plan_cache, torch.Tensor) else 0
+
     def _volume_call(self, forward, src, dst, n_vol, rays_per_vol):
         if self._packed is not None:
             return self._hybrid_call(forward, src, dst, n_vol, rays_per_vol)
@@ -498,10 +535,12 @@ class Operator:
             return
         scratch = self._scratch()
         fn = self._lib.sphrt_forward if forward else self._lib.sphrt_adjoint
+        self._plan_cache_begin()
         with torch.cuda.device(self._cdev):
             _cabi.check(fn(self._tables.c, self._rays.c, src.data_ptr(), _DTYPES[src.dtype],
                            n_vol, rays_per_vol, dst.data_ptr(), scratch.data_ptr(),
                            scratch.numel(), self._stream()))
+        self._plan_cache_end()
 
     # ---- batching rules of Operator.__call__ (raytracer.py:703-713) ---------------------
     def _plan(self, shape):
@@ -615,13 +654,16 @@ class Operator:
                                    dtype=d.dtype, device=self._cdev)
                 scratch = self._scratch()
                 ptr = lambda v: None if v is None else v.data_ptr()
+                self._plan_cache_begin()
                 with torch.cuda.device(self._cdev):
                     rc = self._lib.sphrt_normal(self._tables.c, self._rays.c, d.data_ptr(), _DTYPES[d.dtype],
                                                 n_vol, rpv, out.data_ptr(), ptr(bb), ptr(mm), float(scale),
                                                 grad.data_ptr(), scratch.data_ptr(), scratch.numel(),
                                                 self._stream())
                 if rc == 0:
+                    self._plan_cache_end()
                     return out.reshape(out_shape).to(density.device), grad.reshape(shape).to(density.device)
+                self._plan_pending = None
                 if rc != -1:                               # -1: not served by the warp walker
                     _cabi.check(rc)
             y = self._apply_forward(d)

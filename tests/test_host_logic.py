@@ -27,7 +27,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib = _cabi.load()
-    assert lib.sphrt_version() == 6
+    assert lib.sphrt_version() == 7
     assert lib.sphrt_error_string(-3).decode().startswith("scratch")
     # argument validation happens before any CUDA call
     g = _cabi.Grid(0, 1, 1, 0, *([0] * 7))
