@@ -1483,23 +1483,25 @@ struct PassContext {
     int64_t n_words;
     PlanRec* recs;                       // records of the second-generation warp walker (one chunk)
     // plan cache (sphrt_rays.plan_cache): every chunk's records and counts kept between calls
-    PlanRec* cache_recs = nullptr;       // chunk c at cache_recs + c * chunk
+    PlanRec* cache_recs = nullptr;       // chunk c at cache_recs + c * cache_stride
+    int64_t cache_stride = 0;
     unsigned* cache_counts = nullptr;    // 8 unsigned per chunk: [0] ordinary, [1] all-cones records
     unsigned* cache_totals = nullptr;    // [0], [1]: rays of the two fallback passes
     int cache_state = 0;                 // 1: fill, 2: use
 };
 
 // Layout of a plan cache: [256 B totals][32 B per chunk][listed mask][tracked mask][records]
-struct PlanCacheLayout { int64_t n_chunks, off_counts, off_masks, off_recs, bytes; };
+struct PlanCacheLayout { int64_t n_chunks, off_counts, off_masks, off_recs, stride, bytes; };
 inline PlanCacheLayout plan_cache_layout(int64_t n_rays)
 {
     PlanCacheLayout L;
     const int64_t chunk = warp_chunk_rays();
     L.n_chunks = (n_rays + chunk - 1) / chunk;
+    L.stride = (n_rays < chunk ? n_rays : chunk) + 32;          // records of one chunk
     L.off_counts = 256;
     L.off_masks = (L.off_counts + 32 * L.n_chunks + 255) / 256 * 256;
     L.off_recs = L.off_masks + 2 * mask_bytes(n_rays);
-    L.bytes = L.off_recs + L.n_chunks * (chunk + 32) * (int64_t)sizeof(PlanRec);     // chunk c at c * (chunk + 32)
+    L.bytes = L.off_recs + L.n_chunks * L.stride * (int64_t)sizeof(PlanRec);          // chunk c at c * stride
     return L;
 }
 
@@ -1515,6 +1517,7 @@ inline void attach_plan_cache(PassContext& cx, const sphrt_rays* rays)
     cx.mask_listed = (uint32_t*)(c + L.off_masks);
     cx.mask_tracked = (uint32_t*)(c + L.off_masks + mask_bytes(rays->n_rays));
     cx.cache_recs = (PlanRec*)(c + L.off_recs);
+    cx.cache_stride = L.stride;
     cx.cache_state = (int)rays->plan_cache_state;
 }
 
@@ -1557,7 +1560,7 @@ int launch_warp(const PassContext& cx, const WarpLaunch& wl, const Op& op, unsig
     for (int64_t base = 0; base < cx.kr.n; base += chunk, c++) {
         const int64_t n = cx.kr.n - base < chunk ? cx.kr.n - base : chunk;
         const int64_t cap = (n + 31) / 32 * 32;
-        PlanRec* recs = cached ? cx.cache_recs + c * (chunk + 32) : cx.recs;
+        PlanRec* recs = cached ? cx.cache_recs + c * cx.cache_stride : cx.recs;
         unsigned* cnt = cached ? cx.cache_counts + 8 * c : wc;          // [0] ordinary, [1] all-cones records
         if (base > 0 || cached) cudaMemsetAsync(wc, 0, 4 * sizeof(unsigned), cx.st);
         if (plan_now) {

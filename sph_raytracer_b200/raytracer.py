@@ -401,6 +401,11 @@ class Operator:
         """Pack the segments of the first observations (all of them if ``budget`` is None or they
         fit) at 4 bytes per segment; the other observations stay regenerated (hybrid operator)."""
         r, t = self._rays, self._tables
+        # (the plan cache of the whole ray list is of no use to a hybrid operator: its memory goes
+        # to the packed list)
+        self._plan_cache = False
+        r.c.plan_cache, r.c.plan_cache_bytes, r.c.plan_cache_state = None, 0, 0
+        torch.cuda.empty_cache()             # (hand its segment back before anything is carved out of it)
         count = torch.empty(r.n, dtype=torch.int32, device=self._cdev)
         scratch = self._scratch()
         with torch.cuda.device(self._cdev):
