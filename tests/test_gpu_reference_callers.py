@@ -54,7 +54,7 @@ def _orbit(mod, n):
                for th in torch.linspace(0, 2 * torch.pi, n))
 
 
-@pytest.mark.parametrize("store", [False, "auto"])
+@pytest.mark.parametrize("store", [False, "auto", "fused"])
 def test_reference_gd_loss_and_model_run_unchanged_on_the_cuda_operator(S, R, store):
     """static_retrieval.py:18-57 at full size: 100 Adam iterations of the reference's gd() with its
     SquareLoss + NegRegularizer and FullyDenseModel; only ``Operator`` is this package's."""
@@ -67,6 +67,10 @@ def test_reference_gd_loss_and_model_run_unchanged_on_the_cuda_operator(S, R, st
     x = torch.zeros(grid.shape, device="cuda")
     x[:, 25:, :25] = 1
     x[:, :25, 25:] = 1
+    fused = store == "fused"      # this package's drop-in FusedSquareLoss inside the reference's gd()
+    if fused:
+        from sph_raytracer_b200.loss import FusedSquareLoss as SquareLoss
+        store = False
     op = S.Operator(grid, geoms, device=x.device, store_segments=store)
     meas = op(x)
     stable = torch.ones(meas.shape, dtype=torch.bool)
