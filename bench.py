@@ -441,6 +441,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
         state += sum(v.numel() * v.element_size() for v in r._gen.values() if isinstance(v, torch.Tensor))
     state += (op._tables.nr + op._tables.ne + op._tables.na) * 8 * 8 + op.stored_bytes + op.plan_cache_bytes
     op_bytes = float(state + op._scratch_bytes)
+    plan_cache_bytes = float(op.plan_cache_bytes)
     clocks = sampler.summary() if sampler is not None else None
 
     stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
@@ -453,7 +454,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     tot_seg, tot_rays = sums.tolist()
     return {"op": op, "grid": grid, "local_grid": local_grid, "desc": desc, "sharding": sharding, "dynamic": dynamic,
             "ms": ms, "e2e_ms": e2e_ms if e2e else None, "t_fwd": t_fwd, "t_adj": t_adj, "peak_bytes": peak_bytes,
-            "t_build": t_build, "t_fused": t_fused if fused else None, "op_bytes": op_bytes,
+            "t_build": t_build, "t_fused": t_fused if fused else None, "op_bytes": op_bytes, "plan_cache_bytes": plan_cache_bytes,
             "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
             "launches": launches, "x": x, "y": y, "out": out, "vshape": vshape, "block": (lo, hi), "clocks": clocks,
             "h2d": x_host.numel() * 4 + y_host.numel() * 4, "d2h": out_host.numel() * 4 + grad_host.numel() * 4}
@@ -466,7 +467,7 @@ def config_line(m, world):
             "forward_ms": m["t_fwd"], "adjoint_ms": m["t_adj"], "ms_per_step": ms,
             "ray_segments_per_s": 2 * m["tot_seg"] / (ms / 1e3), "rays_per_s": 2 * m["tot_rays"] / (ms / 1e3),
             "e2e_ms_per_step": m["e2e_ms"], "peak_memory_gb": m["peak_bytes"] / 1e9,
-            "operator_memory_gb": m["op_bytes"] / 1e9,
+            "operator_memory_gb": m["op_bytes"] / 1e9, "plan_cache_gb": m["plan_cache_bytes"] / 1e9,
             "reference_memory_gb": reference_memory_gb(m["grid"], m["tot_rays"]),
             "operator_build_s": m["t_build"], "sharding": m["sharding"], "walker": m["op"].walker(),
             "gpu_launches_per_step": m["launches"] / max(1, m.get("steps", 1)),
@@ -698,6 +699,10 @@ def run_gpu(args):
             # the operator's own part of it (state + scratch of one call; rank 0), the rest being the
             # step's volumes, integrals and gradients incl. the end-to-end copies
             "operator_memory_gb": m["op_bytes"] / 1e9,
+            # ... of which the optional plan cache (80 B per ray, kept after the first call so that later
+            # calls skip the planning kernel; SPHRT_PLAN_CACHE=0 or less than ~7x its size of free
+            # memory: not allocated, ~5 % slower)
+            "plan_cache_gb": m["plan_cache_bytes"] / 1e9,
             # what the reference keeps for the same rays (regs + lens, raytracer.py:17-45) and its own
             # working-set estimator (examples/memory_usage.py:23-44), whole job
             "reference_memory_gb": reference_memory_gb(grid, tot_rays),

@@ -301,9 +301,7 @@ class Operator:
         self._scratch_bytes = int(self._lib.sphrt_scratch_bytes(self._tables.c, self._rays.n))
         self._stored = None
         self._packed = None
-        self._plan_cache = None          # None: not decided yet; False: not used; else the buffer
-        self._plan_key = None
-        self._plan_pending = None
+        self._pc = {}                    # plan caches: "main" (all rays), "suffix" (hybrid operator)
         self._autotune()
         if isinstance(store_segments, str):
             if store_segments not in ("packed", "auto"):
@@ -403,7 +401,7 @@ class Operator:
         r, t = self._rays, self._tables
         # (the plan cache of the whole ray list is of no use to a hybrid operator: its memory goes
         # to the packed list)
-        self._plan_cache = False
+        self._pc = {"main": {"buf": False, "key": None, "pending": None}}
         r.c.plan_cache, r.c.plan_cache_bytes, r.c.plan_cache_state = None, 0, 0
         torch.cuda.empty_cache()             # (hand its segment back before anything is carved out of it)
         count = torch.empty(r.n, dtype=torch.int32, device=self._cdev)
@@ -485,47 +483,55 @@ class Operator:
                                        _DTYPES[a.dtype], nv, rays_per_vol, t.nvox, b.data_ptr(), self._stream()))
                 else:
                     scratch = torch.empty(max(self._suffix_scratch_bytes, 8), dtype=torch.uint8, device=self._cdev)
+                    self._plan_cache_begin("suffix")
                     _cabi.check(traced(t.c, self._suffix, a.data_ptr(), _DTYPES[a.dtype], nv, rays_per_vol,
                                        b.data_ptr(), scratch.data_ptr(), scratch.numel(), self._stream()))
+                    self._plan_cache_end("suffix")
                 parts.append((lo, hi, blk, whole))
         if forward and not flat:
             for lo, hi, blk, whole in parts:
                 if not whole:
                     dst[:, lo:hi] = blk
 
-    def _plan_cache_begin(self):
+    def _plan_cache_begin(self, which="main"):
         """Plan cache of the warp walker (``sphrt_rays.plan_cache``): the planner's 80-byte record per
         ray and its two bits per ray are the same in every call, so they are kept after the first
         one if that costs less than 15 % of the free device memory (SPHRT_PLAN_CACHE=0: never).
-        Returns the state to restore after the call."""
+        ``which``: the operator's whole ray list, or the regenerated suffix of a hybrid operator."""
         import os
-        if self._plan_cache is False or os.environ.get("SPHRT_PLAN_CACHE", "1") == "0":
-            self._rays.c.plan_cache_state = 0
+        c = self._pc.setdefault(which, {"buf": None, "key": None, "pending": None})
+        rays = self._rays.c if which == "main" else self._suffix
+        n = self._rays.n if which == "main" else int(rays.n_rays)
+        if c["buf"] is False or os.environ.get("SPHRT_PLAN_CACHE", "1") == "0":
+            rays.plan_cache_state = 0
             return
         key = tuple(os.environ.get(k) for k in ("SPHRT_WARP_CHUNK", "SPHRT_WALKER", "SPHRT_COOP_GEN", "SPHRT_AUTOTUNE"))
-        if self._plan_cache is None:
-            nbytes = int(self._lib.sphrt_plan_cache_bytes(self._tables.c, self._rays.n))
+        if c["buf"] is None:
+            nbytes = int(self._lib.sphrt_plan_cache_bytes(self._tables.c, n))
             if nbytes == 0 or self.walker() != "cooperative" or \
                     nbytes > 0.15 * torch.cuda.mem_get_info(self._cdev)[0]:
-                self._plan_cache = False
+                c["buf"] = False
                 return
-            self._plan_cache = torch.empty(nbytes, dtype=torch.uint8, device=self._cdev)
-            self._rays.c.plan_cache = self._plan_cache.data_ptr()
-            self._rays.c.plan_cache_bytes = nbytes
-            self._plan_key = None
-        if key != self._plan_key:            # first call, or the environment picked another kernel path
-            self._plan_pending = key         # (becomes the cache's key once the call has succeeded)
-            self._rays.c.plan_cache_state = 1
+            c["buf"] = torch.empty(nbytes, dtype=torch.uint8, device=self._cdev)
+            rays.plan_cache = c["buf"].data_ptr()
+            rays.plan_cache_bytes = nbytes
+            c["key"] = None
+        if key != c["key"]:                  # first call, or the environment picked another kernel path
+            c["pending"] = key               # (becomes the cache's key once the call has succeeded)
+            rays.plan_cache_state = 1
         else:
-            self._rays.c.plan_cache_state = 2
+            rays.plan_cache_state = 2
 
-    def _plan_cache_end(self):
-        if getattr(self, "_plan_pending", None) is not None:
-            self._plan_key, self._plan_pending = self._plan_pending, None
+    def _plan_cache_end(self, which="main", ok=True):
+        c = self._pc.get(which)
+        if c is not None and c["pending"] is not None:
+            if ok:
+                c["key"] = c["pending"]
+            c["pending"] = None
 
     @property
     def plan_cache_bytes(self):
-        return self._plan_cache.numel() if isinstance(self._plan_cache, torch.Tensor) else 0
+        return sum(c["buf"].numel() for c in self._pc.values() if isinstance(c["buf"], torch.Tensor))
 
     def _volume_call(self, forward, src, dst, n_vol, rays_per_vol):
         if self._packed is not None:
@@ -665,10 +671,9 @@ class Operator:
                                                 n_vol, rpv, out.data_ptr(), ptr(bb), ptr(mm), float(scale),
                                                 grad.data_ptr(), scratch.data_ptr(), scratch.numel(),
                                                 self._stream())
+                self._plan_cache_end(ok=rc == 0)
                 if rc == 0:
-                    self._plan_cache_end()
                     return out.reshape(out_shape).to(density.device), grad.reshape(shape).to(density.device)
-                self._plan_pending = None
                 if rc != -1:                               # -1: not served by the warp walker
                     _cabi.check(rc)
             y = self._apply_forward(d)
