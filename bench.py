@@ -405,8 +405,21 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
         copy = torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
 
+        # The volume is ONE input of the job, replicated over the ranks: rank 0 uploads it and the
+        # others receive it over NVLink (NCCL broadcast); likewise the gradient, the job's ONE result
+        # besides the integrals, is reduced to rank 0 and downloaded there.  Every rank uploads its own
+        # measurements and downloads its own integrals.  (A dynamic volume is sharded by time-slice:
+        # every rank moves its own slices.)
+        replicated = reduce_grad
+
         def step_e2e():
-            xd = x_host.to(dev, non_blocking=True).requires_grad_(True)
+            if replicated and rank != 0:
+                xd = torch.empty(vshape, device=dev)
+            else:
+                xd = x_host.to(dev, non_blocking=True)
+            if replicated:
+                dist.broadcast(xd, 0)
+            xd.requires_grad_(True)
             with torch.cuda.stream(copy):
                 wd = y_host.to(dev, non_blocking=True)
                 up = torch.cuda.Event(); up.record(copy)
@@ -418,9 +431,10 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
             main.wait_event(up)
             yy.backward(wd)                                  # autograd adjoint
             gd = xd.grad
-            if reduce_grad:
-                dist.all_reduce(gd)
-            grad_host.copy_(gd, non_blocking=True)
+            if replicated:
+                dist.reduce(gd, 0)
+            if not replicated or rank == 0:
+                grad_host.copy_(gd, non_blocking=True)
             copy.synchronize(); main.synchronize()
 
         step_e2e()
@@ -446,18 +460,22 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
 
     stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
                          dtype=torch.float64, device=dev)
-    sums = torch.tensor([float(n_seg), float(n_rays)], dtype=torch.float64, device=dev)
+    # bytes this rank moves per end-to-end step (whole job: summed over the ranks below)
+    moves_volume = not (world > 1 and not dynamic) or rank == 0
+    h2d = y_host.numel() * 4 + (x_host.numel() * 4 if moves_volume else 0)
+    d2h = out_host.numel() * 4 + (grad_host.numel() * 4 if moves_volume else 0)
+    sums = torch.tensor([float(n_seg), float(n_rays), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     ms, e2e_ms, t_fwd, t_adj, peak_bytes, t_build, t_fused = stats.tolist()
-    tot_seg, tot_rays = sums.tolist()
+    tot_seg, tot_rays, h2d, d2h = sums.tolist()
     return {"op": op, "grid": grid, "local_grid": local_grid, "desc": desc, "sharding": sharding, "dynamic": dynamic,
             "ms": ms, "e2e_ms": e2e_ms if e2e else None, "t_fwd": t_fwd, "t_adj": t_adj, "peak_bytes": peak_bytes,
             "t_build": t_build, "t_fused": t_fused if fused else None, "op_bytes": op_bytes, "plan_cache_bytes": plan_cache_bytes,
             "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
             "launches": launches, "x": x, "y": y, "out": out, "vshape": vshape, "block": (lo, hi), "clocks": clocks,
-            "h2d": x_host.numel() * 4 + y_host.numel() * 4, "d2h": out_host.numel() * 4 + grad_host.numel() * 4}
+            "h2d": h2d, "d2h": d2h}
 
 
 def config_line(m, world):
@@ -687,7 +705,10 @@ def run_gpu(args):
                          "algorithmic_bytes": f"{per[0]} B/segment + {per[1]} B/ray + {per[2]} B/voxel"},
             "e2e": {"value": 2 * tot_seg / (e2e_step / 1e3), "unit": "ray-segments/s",
                     "ms_per_step": e2e_step, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
-                    "path": "Operator.__call__ + autograd backward, pinned host buffers, copies overlapped on a copy stream"},
+                    "path": "Operator.__call__ + autograd backward, pinned host buffers, copies overlapped on a copy stream; "
+                            "bytes are the whole job's: with N > 1 the replicated volume is uploaded by rank 0 and "
+                            "broadcast over NVLink, the gradient reduced to rank 0 and downloaded there, every rank "
+                            "moves its own measurements and integrals"},
             # counted by the library itself (sphrt_launch_count): every kernel it launched in the timed steps
             "gpu_launches": int(m["launches"]),
             "walker": op.walker(),
