@@ -199,8 +199,15 @@ SPHRT_HD void cone_roots(const ConeQuad& q, double delta, double& t1, double& t2
 SPHRT_HD void cone_roots_guarded(const ConeQuad& q, double delta, double& t1, double& t2)
 {
     const bool none = !(delta >= 0);
-    // (sqrt(0) itself takes the slow path too: 1.0 stands in for both and the zero is put back)
-    double sq = sqrt(none || delta == 0 ? 1.0 : delta);
+    // (sqrt(0) itself takes the slow path too: 1.0 stands in for both and the zero is put back.
+    // The empty asm keeps the select in FRONT of the square root: the compiler otherwise takes
+    // sqrt(delta) first and selects afterwards, which is the same value and the slow path again --
+    // 0.75 calls per config-5 ray, one lane each.)
+    double arg = (none || delta == 0) ? 1.0 : delta;
+#ifdef __CUDA_ARCH__
+    asm("" : "+d"(arg));
+#endif
+    double sq = sqrt(arg);
     if (delta == 0) sq = 0.0;
     t1 = (-q.bb + sq) / (2 * q.aa);
     t2 = (-q.bb - sq) / (2 * q.aa);
