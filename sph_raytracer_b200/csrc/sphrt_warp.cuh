@@ -34,6 +34,17 @@
 
 namespace sphrt {
 
+// Stage 2 loads only the head it consumed again (two selects more, one shared-memory load less per
+// event: the walking kernels keep the LSU data pipe 85-91 % busy, two thirds of it shared-memory
+// wavefronts at 2-3x their conflict-free count -- per-lane list positions are as good as random
+// banks; forward -2.6 %, adjoint -2.4 %).  The same in stage 1 (SPHRT_ONE_HEAD1) pays for its six
+// selects with all it saves.
+#ifndef SPHRT_ONE_HEAD
+#define SPHRT_ONE_HEAD 1
+#endif
+#ifndef SPHRT_ONE_HEAD1
+#define SPHRT_ONE_HEAD1 0
+#endif
 #ifndef SPHRT_WARP_DEPTH
 #define SPHRT_WARP_DEPTH 4
 #endif
@@ -487,13 +498,23 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
         const uint32_t rE1 = rE - 4u;
         int left = nEA - g0;                           // live entries of this share (may be <= 0)
         bool tx = xv <= yv;
+        int se = 0, sa = 0;
+        if (SPHRT_ONE_HEAD1) { se = lds_s32(rE1 + 4u * sE); sa = lds_s32(cAr - 4u * sE); }
 #define SPHRT_STAGE1_STEP(K)                                                                      \
         {                                                                                         \
             const double t = tx ? xv : yv;                                                        \
             sE += tx ? 1 : 0;                                                                     \
-            xv = lds_f64(tE + 8u * sE);                                                           \
-            yv = lds_f64(cAt + 8u * ((K) + 1) - 8u * sE);                                         \
-            const int st = lds_s32(rE1 + 4u * sE) + lds_s32(cAr + 4u * ((K) + 1) - 4u * sE) + base_r; \
+            if (SPHRT_ONE_HEAD1) {                 /* only the consumed head / state is loaded again */ \
+                const double v = lds_f64(tx ? tE + 8u * sE : cAt + 8u * ((K) + 1) - 8u * sE);     \
+                const int ns = lds_s32(tx ? rE1 + 4u * sE : cAr + 4u * ((K) + 1) - 4u * sE);      \
+                xv = tx ? v : xv; yv = tx ? yv : v;                                               \
+                se = tx ? ns : se; sa = tx ? sa : ns;                                             \
+            } else {                                                                              \
+                xv = lds_f64(tE + 8u * sE);                                                       \
+                yv = lds_f64(cAt + 8u * ((K) + 1) - 8u * sE);                                     \
+                se = lds_s32(rE1 + 4u * sE); sa = lds_s32(cAr + 4u * ((K) + 1) - 4u * sE);        \
+            }                                                                                     \
+            const int st = se + sa + base_r;                                                      \
             const bool live = (K) < left;          /* beyond the end the heads are stale memory */ \
             viol |= live && (xv < t || yv < t);                                                   \
             if (live) { sts_f64(oT + 8u * (K), t); sts_s32(oS + 4u * (K), st); }                  \
@@ -577,8 +598,13 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
 #define SPHRT_WARP_STEP(SLOT, K)                                                                  \
         {                                                                                         \
             u += tx ? 1 : 0;                                                                      \
-            xv = lds_f64(cR + 8u * u);                                                            \
-            yv = lds_f64(cE + 8u * ((K) + 1) - 8u * u);                                           \
+            if (SPHRT_ONE_HEAD) {                  /* only the consumed head is loaded again */    \
+                const double v = lds_f64(tx ? cR + 8u * u : cE + 8u * ((K) + 1) - 8u * u);        \
+                xv = tx ? v : xv; yv = tx ? yv : v;                                               \
+            } else {                                                                              \
+                xv = lds_f64(cR + 8u * u);                                                        \
+                yv = lds_f64(cE + 8u * ((K) + 1) - 8u * u);                                       \
+            }                                                                                     \
             const int sea = lds_s32(cS + 4u * ((K) + 1) - 4u * u);                                \
             const unsigned idx = (unsigned)((u < 0 ? -u : u) * nena + sea);                       \
             tx = xv <= yv;                                                                        \
