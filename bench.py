@@ -740,6 +740,16 @@ def run_gpu(args):
                                       "peak_thread_inst_per_s": issue_peak,
                                       "frac": ti * seg_r / (t_dom / 1e3) / issue_peak,
                                       "source": "ncu smsp__thread_inst_executed of the dominant kernel (profiles/r2_kernel_profile.json)"}
+        # ... and the unit that is busier still: the LSU data pipe (shared-memory wavefronts of the list
+        # merges plus the gathers / reductions), as ncu measured it on the profiled launch
+        lsu = prof.get("lsu_data_pipe_pct")
+        if lsu:
+            line["lsu_data_pipe"] = {"busy_frac": {k: lsu[k] / 100 for k in ("forward", "adjoint")},
+                                     "shared_memory_share": {k: lsu["of_which_shared_memory"][k] / 100
+                                                             for k in ("forward", "adjoint")},
+                                     "source": "ncu l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed, "
+                                               "16 config-5 observations (profiles/r2_kernel_profile.json); "
+                                               "not re-measured by this run"}
         # the bandwidth-side bounds that are near: one L2 gather / one L2 fp32 reduction per
         # segment against the measured peaks of tools/microbench/peaks.cu (profiles/)
         try:

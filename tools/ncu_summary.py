@@ -11,6 +11,10 @@ KEYS = ['gpu__time_duration.sum', 'launch__block_size', 'launch__grid_size', 'la
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum',
         'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'memory_l1_wavefronts_shared_ideal',
+        'sass__inst_executed_shared_loads', 'sass__inst_executed_shared_stores',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
