@@ -405,22 +405,34 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
         copy = torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
 
-        # The volume is ONE input of the job, replicated over the ranks: rank 0 uploads it and the
-        # others receive it over NVLink (NCCL broadcast); likewise the gradient, the job's ONE result
-        # besides the integrals, is reduced to rank 0 and downloaded there.  Every rank uploads its own
+        # The volume is ONE input of the job, replicated over the ranks, and every rank's host holds
+        # it (SPMD): each rank uploads 1/N of it and the slices are all-gathered over NVLink; likewise
+        # the gradient, the job's ONE result besides the integrals, is reduce-scattered and each rank
+        # downloads its 1/N into its own pinned buffer (the bytes over PCIe are those of ONE volume
+        # each way, spread over the N links).  A volume that does not divide by N goes up from rank 0
+        # and is broadcast, its gradient is reduced to rank 0.  Every rank uploads its own
         # measurements and downloads its own integrals.  (A dynamic volume is sharded by time-slice:
         # every rank moves its own slices.)
         replicated = reduce_grad
+        sliced = replicated and x_host.numel() % world == 0
+        per = x_host.numel() // world if sliced else 0
+        xs_host = x_host.view(-1)[rank * per:(rank + 1) * per] if sliced else None
+        gs_host = grad_host.view(-1)[rank * per:(rank + 1) * per] if sliced else None
 
         def step_e2e():
-            if replicated and rank != 0:
+            if sliced:
+                xd = torch.empty(vshape, device=dev)
+                dist.all_gather_into_tensor(xd.view(-1), xs_host.to(dev, non_blocking=True))
+            elif replicated and rank != 0:
                 xd = torch.empty(vshape, device=dev)
             else:
                 xd = x_host.to(dev, non_blocking=True)
-            if replicated:
+            if replicated and not sliced:
                 dist.broadcast(xd, 0)
             xd.requires_grad_(True)
+            x_up = torch.cuda.Event(); x_up.record(main)
             with torch.cuda.stream(copy):
+                copy.wait_event(x_up)                        # (the volume has the link to itself first)
                 wd = y_host.to(dev, non_blocking=True)
                 up = torch.cuda.Event(); up.record(copy)
             yy = op(xd)                                      # Operator.__call__ (autograd node)
@@ -431,10 +443,15 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
             main.wait_event(up)
             yy.backward(wd)                                  # autograd adjoint
             gd = xd.grad
-            if replicated:
-                dist.reduce(gd, 0)
-            if not replicated or rank == 0:
-                grad_host.copy_(gd, non_blocking=True)
+            if sliced:
+                gpart = torch.empty(per, device=dev)
+                dist.reduce_scatter_tensor(gpart, gd.view(-1))
+                gs_host.copy_(gpart, non_blocking=True)
+            else:
+                if replicated:
+                    dist.reduce(gd, 0)
+                if not replicated or rank == 0:
+                    grad_host.copy_(gd, non_blocking=True)
             copy.synchronize(); main.synchronize()
 
         step_e2e()
@@ -444,6 +461,20 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
             step_e2e()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+        # what came back is what the device-resident path computes (same kernels; the sums over the
+        # ranks run in NCCL's order, hence a tolerance for the gradient)
+        with torch.no_grad():
+            ref_y = op(x)
+            assert torch.equal(out_host, ref_y.cpu()), "end-to-end integrals differ from the device-resident path"
+            ref_g = op.T(y)
+            if reduce_grad:
+                dist.all_reduce(ref_g)
+            ref_g = ref_g.reshape(-1)
+            got = gs_host if sliced else grad_host.view(-1)
+            want = ref_g[rank * per:(rank + 1) * per] if sliced else ref_g
+            if sliced or not replicated or rank == 0:
+                assert torch.allclose(got, want.cpu(), rtol=1e-4, atol=1e-4 * float(ref_g.abs().max())), \
+                    "end-to-end gradient differs from the device-resident path"
     peak_bytes = torch.cuda.max_memory_allocated(dev) - mem_base
     # what of that peak is the operator's own: its persistent state (grid tables, detector frames or
     # ray directions, start cells, a stored list if any) and the scratch of one call (ray masks,
@@ -461,9 +492,13 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
                          dtype=torch.float64, device=dev)
     # bytes this rank moves per end-to-end step (whole job: summed over the ranks below)
-    moves_volume = not (world > 1 and not dynamic) or rank == 0
-    h2d = y_host.numel() * 4 + (x_host.numel() * 4 if moves_volume else 0)
-    d2h = out_host.numel() * 4 + (grad_host.numel() * 4 if moves_volume else 0)
+    replicated_volume = world > 1 and not dynamic
+    if replicated_volume and x_host.numel() % world == 0:
+        vol_bytes = x_host.numel() // world * 4                  # this rank's slice
+    else:
+        vol_bytes = x_host.numel() * 4 if (not replicated_volume or rank == 0) else 0
+    h2d = y_host.numel() * 4 + vol_bytes
+    d2h = out_host.numel() * 4 + vol_bytes
     sums = torch.tensor([float(n_seg), float(n_rays), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -706,9 +741,10 @@ def run_gpu(args):
             "e2e": {"value": 2 * tot_seg / (e2e_step / 1e3), "unit": "ray-segments/s",
                     "ms_per_step": e2e_step, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
                     "path": "Operator.__call__ + autograd backward, pinned host buffers, copies overlapped on a copy stream; "
-                            "bytes are the whole job's: with N > 1 the replicated volume is uploaded by rank 0 and "
-                            "broadcast over NVLink, the gradient reduced to rank 0 and downloaded there, every rank "
-                            "moves its own measurements and integrals"},
+                            "bytes are the whole job's: with N > 1 every rank uploads 1/N of the replicated volume "
+                            "(all-gathered over NVLink) and downloads 1/N of the reduce-scattered gradient, and "
+                            "moves its own measurements and integrals; results checked against the "
+                            "device-resident path after the timed steps"},
             # counted by the library itself (sphrt_launch_count): every kernel it launched in the timed steps
             "gpu_launches": int(m["launches"]),
             "walker": op.walker(),
