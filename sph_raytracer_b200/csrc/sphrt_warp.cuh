@@ -42,6 +42,9 @@ namespace sphrt {
 #ifndef SPHRT_ONE_HEAD
 #define SPHRT_ONE_HEAD 1
 #endif
+#ifndef SPHRT_SKEW1
+#define SPHRT_SKEW1 1
+#endif
 #ifndef SPHRT_ONE_HEAD1
 #define SPHRT_ONE_HEAD1 0
 #endif
@@ -483,8 +486,16 @@ __device__ __forceinline__ int warp_walk_ray(const Tab32& T, const WarpPlan& P, 
     const int nena = T.ne * na;
     const int base_r = (R.imin - 1) * nena;
     {
+#if SPHRT_SKEW1
+        // shares of c1 or c1 - 1 entries (every fourth lane): with equal shares of an even size the
+        // lanes' output slots fall on a few banks.  A lane with the shorter share writes the first
+        // entry of the next one as well -- the same values.
+        const int c1 = (nEA + 38) >> 5;
+        const int g0 = lane * c1 - (lane >> 2);
+#else
         const int c1 = (nEA + 31) >> 5;
         const int g0 = lane * c1;
+#endif
         const int gs = g0 < nEA ? g0 : nEA;
         const int nmin = nE < nA ? nE : nA;
         int sE = warp_corank(tE, nE, tA, nA, gs, 32 - __clz(nmin > 0 ? nmin : 1));   // E events taken
