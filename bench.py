@@ -401,6 +401,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     # the upload of the adjoint input rides a copy stream under the forward pass, the download of
     # the integrals under the adjoint pass
     e2e_ms = None
+    e2e_bad, e2e_gerr = 0.0, 0.0
     if e2e:
         copy = torch.cuda.Stream(dev)
         main = torch.cuda.current_stream(dev)
@@ -465,7 +466,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
         # ranks run in NCCL's order, hence a tolerance for the gradient)
         with torch.no_grad():
             ref_y = op(x)
-            assert torch.equal(out_host, ref_y.cpu()), "end-to-end integrals differ from the device-resident path"
+            e2e_bad = 0.0 if torch.equal(out_host, ref_y.cpu()) else 1.0
             ref_g = op.T(y)
             if reduce_grad:
                 dist.all_reduce(ref_g)
@@ -473,8 +474,7 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
             got = gs_host if sliced else grad_host.view(-1)
             want = ref_g[rank * per:(rank + 1) * per] if sliced else ref_g
             if sliced or not replicated or rank == 0:
-                assert torch.allclose(got, want.cpu(), rtol=1e-4, atol=1e-4 * float(ref_g.abs().max())), \
-                    "end-to-end gradient differs from the device-resident path"
+                e2e_gerr = float((got - want.cpu()).abs().max() / ref_g.abs().max().clamp_min(1e-30))
     peak_bytes = torch.cuda.max_memory_allocated(dev) - mem_base
     # what of that peak is the operator's own: its persistent state (grid tables, detector frames or
     # ray directions, start cells, a stored list if any) and the scratch of one call (ray masks,
@@ -489,8 +489,8 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     plan_cache_bytes = float(op.plan_cache_bytes)
     clocks = sampler.summary() if sampler is not None else None
 
-    stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, e2e_ms or 0.0, t_fwd, t_adj, float(peak_bytes), t_build, t_fused or 0.0,
+                          e2e_bad, e2e_gerr], dtype=torch.float64, device=dev)
     # bytes this rank moves per end-to-end step (whole job: summed over the ranks below)
     replicated_volume = world > 1 and not dynamic
     if replicated_volume and x_host.numel() % world == 0:
@@ -503,14 +503,18 @@ def measure(name, obs, steps, warmup, world, rank, dev, flush=None, e2e=True, sa
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, t_fwd, t_adj, peak_bytes, t_build, t_fused = stats.tolist()
+    ms, e2e_ms, t_fwd, t_adj, peak_bytes, t_build, t_fused, e2e_bad, e2e_gerr = stats.tolist()
     tot_seg, tot_rays, h2d, d2h = sums.tolist()
     return {"op": op, "grid": grid, "local_grid": local_grid, "desc": desc, "sharding": sharding, "dynamic": dynamic,
             "ms": ms, "e2e_ms": e2e_ms if e2e else None, "t_fwd": t_fwd, "t_adj": t_adj, "peak_bytes": peak_bytes,
             "t_build": t_build, "t_fused": t_fused if fused else None, "op_bytes": op_bytes, "plan_cache_bytes": plan_cache_bytes,
             "tot_seg": tot_seg, "tot_rays": tot_rays, "n_seg": n_seg, "n_rays": n_rays,
             "launches": launches, "x": x, "y": y, "out": out, "vshape": vshape, "block": (lo, hi), "clocks": clocks,
-            "h2d": h2d, "d2h": d2h}
+            "h2d": h2d, "d2h": d2h,
+            # the end-to-end results against the device-resident path (same kernels): integrals bit for
+            # bit, gradient up to the order of its float32 sums (max |difference| / max |gradient|)
+            "e2e_check": {"integrals_equal": e2e_bad == 0.0, "gradient_max_rel_diff": e2e_gerr,
+                          "ok": e2e_bad == 0.0 and e2e_gerr < 1e-4} if e2e else None}
 
 
 def config_line(m, world):
@@ -740,6 +744,7 @@ def run_gpu(args):
                          "algorithmic_bytes": f"{per[0]} B/segment + {per[1]} B/ray + {per[2]} B/voxel"},
             "e2e": {"value": 2 * tot_seg / (e2e_step / 1e3), "unit": "ray-segments/s",
                     "ms_per_step": e2e_step, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
+                    "check": m["e2e_check"],
                     "path": "Operator.__call__ + autograd backward, pinned host buffers, copies overlapped on a copy stream; "
                             "bytes are the whole job's: with N > 1 every rank uploads 1/N of the replicated volume "
                             "(all-gathered over NVLink) and downloads 1/N of the reduce-scattered gradient, and "
