@@ -332,6 +332,14 @@ class Operator:
         if os.environ.get("SPHRT_AUTOTUNE", "1") == "0" or os.environ.get("SPHRT_WALKER") or self._rays.n < 4096:
             return
         r, t = self._rays, self._tables
+        # Grids on which the library's size heuristic already takes the cooperative walker (a ray meets
+        # a few hundred boundaries: it is 2-3x the per-thread walker there) are not measured: the
+        # choice is the same in every process -- also under a profiler, whose per-launch overhead
+        # would weigh on the path with more launches.
+        if int(self._lib.sphrt_walker_kind(t.c, r.n)) == 1:
+            r.c.walker = 1
+            self.autotune = {"walker": "cooperative", "ms": 0.0, "cached": False, "decided_by": "size heuristic"}
+            return
         # one decision per (grid shape, detector shape, device): operators built again for the same
         # problem (a retrieval script, the bench's repetitions) reuse it and stay deterministic
         key = (t.nr, t.ne, t.na, tuple(r.shape), r._gen is not None, str(self._cdev))
